@@ -1,0 +1,164 @@
+/* rmb.h -- C ABI of libraymarch_b200.so, the B200-native replacement for the WebGL2 layer under
+ * radian628/raymarching-engine's render-job API.
+ *
+ * The reference's TypeScript host (client/src/renderer/*.tsx) talks to the GPU only through a
+ * WebGL2RenderingContext.  Each entry point below replaces one group of those calls; the
+ * reference interface it stands in for is cited as file:line under /root/reference/client/src.
+ * An N-API addon maps these 1:1 into JavaScript; the tests drive the same
+ * symbols through Python ctypes.
+ *
+ * Conventions: plain pointers and sizes only; no exceptions cross the boundary; every function
+ * that can fail returns an rmb_status and leaves a message retrievable with rmb_last_error().
+ * Images are row-major with row 0 at the BOTTOM (OpenGL convention), RGBA interleaved.
+ * One context drives one GPU (one process per GPU; multi-GPU jobs shard rows, see rank/n_ranks).
+ * All calls are asynchronous on the context's stream except rmb_present, rmb_fb_read,
+ * rmb_counters_read, rmb_sync and rmb_ctx_destroy.
+ */
+#ifndef RMB_H_
+#define RMB_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RMB_ABI_VERSION 1
+
+typedef struct rmb_ctx rmb_ctx;         /* RenderJobContext            renderer/RenderJobExecutor.tsx:32-54 */
+typedef struct rmb_program rmb_program; /* WebGLProgram (raymarcher)   renderer/ShaderCache.tsx:91-119      */
+typedef struct rmb_fb rmb_fb;           /* RenderJobFramebufferInfo    renderer/RenderJobExecutor.tsx:14-30 */
+
+typedef enum rmb_status {
+    RMB_OK = 0,
+    RMB_ERR_FRAGMENT = 1, /* scene failed to compile: ShaderError{type:"fragment"}  ShaderCache.tsx:8-11, :26-33 */
+    RMB_ERR_PROGRAM = 2,  /* module load / link failure: ShaderError{type:"program"} ShaderCache.tsx:66-73      */
+    RMB_ERR_GENERAL = 3,  /* {type:"general"} e.g. "Failed to load framebuffers."   RenderJobExecutor.tsx:73-75 */
+    RMB_ERR_INVALID = 4   /* bad argument (null handle, unknown enum)                                           */
+} rmb_status;
+
+/* rmb_program_get flavours */
+#define RMB_FLAVOUR_EXACT 0 /* scene arithmetic = unfused IEEE fp32, bit-identical to the CPU oracle */
+#define RMB_FLAVOUR_FAST 1  /* scene arithmetic may use FMA contraction and approximate intrinsics   */
+
+/* uniform base types, renderer/Uniforms.tsx:7-9 ("f" | "i" | "ui") */
+#define RMB_UNIFORM_F 0
+#define RMB_UNIFORM_I 1
+#define RMB_UNIFORM_UI 2
+
+/* A scene uniform whose value is baked into the compiled program (uniform specialisation,
+ * SURVEY.md H3).  `data` holds `count` values of the given base type. */
+typedef struct rmb_spec_uniform {
+    const char* name;
+    int type;  /* RMB_UNIFORM_* */
+    int count; /* 1..4 */
+    union {
+        float f[4];
+        int32_t i[4];
+        uint32_t u[4];
+    } data;
+} rmb_spec_uniform;
+
+int rmb_abi_version(void);
+
+/* ---- context -------------------------------------------------------------------------------
+ * replaces loadRenderJobContext(gl)                     renderer/LoadRenderJobContext.tsx:268-287
+ * and canvas.getContext("webgl2")                       index.tsx:106-108
+ * device: CUDA ordinal.  rank/n_ranks/tile_rows: this context renders the row tiles t (of
+ * tile_rows rows each) with t % n_ranks == rank; n_ranks = 1 renders everything.
+ * Returns NULL on failure (the reference returns undefined); rmb_last_error(NULL) explains. */
+rmb_ctx* rmb_ctx_create(int device, int rank, int n_ranks, int tile_rows);
+void rmb_ctx_destroy(rmb_ctx* ctx);
+const char* rmb_last_error(rmb_ctx* ctx);
+/* cudaStream_t all work of this context is enqueued on (for CUDA-event timing by the caller) */
+void* rmb_ctx_stream(rmb_ctx* ctx);
+rmb_status rmb_sync(rmb_ctx* ctx);
+
+/* ---- programs ------------------------------------------------------------------------------
+ * replaces programCache.getProgram(vsrc, fsrc.replace("//SCENESDFHERE", addDefaultFunctions(scene)))
+ *                                                       renderer/RenderJobExecutor.tsx:121-127
+ *          addDefaultFunctionsToShaderCode              settings/shader-editor/Validate.tsx:8-57
+ *          createShaderFromSource / createProgram...    renderer/ShaderCache.tsx:13-119
+ * Lowers the scene GLSL to CUDA C++, NVRTC-compiles it for sm_100a and caches the result by
+ * (source, flavour, baked uniform values).  Compile errors are VALUES: the call returns
+ * RMB_ERR_FRAGMENT / RMB_ERR_PROGRAM, writes "fragment" / "program" / "general" to err_type
+ * (>= 16 bytes) and a GL-style info log ("ERROR: 0:<line>: ...", line numbered like the spliced
+ * reference shader so that the editor's `line - 145` mapping, GLSLEditor.tsx:134-136, holds) to
+ * infolog.  The program handle is owned by the context. */
+rmb_status rmb_program_get(rmb_ctx* ctx, const char* scene_glsl, size_t scene_len, int flavour,
+                           const rmb_spec_uniform* spec, int n_spec, rmb_program** out_program,
+                           char* err_type, char* infolog, size_t infolog_cap);
+/* generated CUDA C++ translation unit (debugging / tests); owned by the program */
+const char* rmb_program_source(rmb_program* prog);
+/* registers per thread / local-memory bytes of the kernels (0 preview, 1 full); -1 if unknown */
+int rmb_program_kernel_attr(rmb_program* prog, int kernel, int* regs, int* local_bytes);
+
+/* ---- uniforms ------------------------------------------------------------------------------
+ * replaces setUniforms(gl, program, {name: UniformData}) renderer/Uniforms.tsx:34-46
+ *          gl.uniform1fv / uniform3fv on arrays          renderer/RenderJobExecutor.tsx:268-291
+ *          gl.uniformMatrix4fv(loc, false, m)            renderer/RenderJobExecutor.tsx:293-297
+ * Unknown names are ignored like a null uniform location (returns RMB_OK).  Values persist per
+ * program until overwritten, as GL uniform state does; they reach __constant__
+ * memory asynchronously before the next rmb_render_sample.  Setting a baked uniform to a value
+ * different from the baked one returns RMB_ERR_INVALID (ask rmb_program_get for a new variant). */
+rmb_status rmb_uniform_set(rmb_program* prog, const char* name, int type, int count, const void* data);
+rmb_status rmb_uniform_set_array(rmb_program* prog, const char* name, int type, int components,
+                                 int n_elements, const void* data);
+rmb_status rmb_uniform_matrix4(rmb_program* prog, const char* name, const float* m16_column_major);
+
+/* ---- framebuffer pool ----------------------------------------------------------------------
+ * replaces context.fbo.create / context.fbo.delete       renderer/LoadRenderJobContext.tsx:184-249
+ * Same semantics: get-or-create by (w, h, frameid); a released set waits in a 3-entry
+ * "purgatory" and is reused for the next acquire of the same size, cleared to zero iff the
+ * frameid differs; new sets start zeroed.  Accumulator formats follow
+ * LoadRenderJobContext.tsx:50-124: colour RGBA32F, normal+dofRadius RGBA16F, albedo+depth RGBA16F.
+ * Returns NULL when allocation fails ("Failed to load framebuffers."). */
+rmb_fb* rmb_fb_acquire(rmb_ctx* ctx, int width, int height, int64_t frameid);
+void rmb_fb_release(rmb_ctx* ctx, int width, int height, int64_t frameid);
+/* number of rows this rank owns (== height when n_ranks == 1) and their global row indices */
+int rmb_fb_local_rows(rmb_fb* fb);
+int rmb_fb_global_row(rmb_fb* fb, int local_row);
+
+/* ---- draw ----------------------------------------------------------------------------------
+ * replaces gl.scissor + the raymarcher drawArrays + the blit drawArrays of one sample
+ *                                                       renderer/RenderJobExecutor.tsx:181-326
+ * (sx, sy, sw, sh) is a GL scissor box: x, y, WIDTH, HEIGHT, clipped to the framebuffer.  The
+ * kernel accumulates in place, which equals draw-into-curr followed by blit-to-prev. */
+rmb_status rmb_render_sample(rmb_ctx* ctx, rmb_program* prog, rmb_fb* fb, int sx, int sy, int sw, int sh);
+
+/* ---- present / readback --------------------------------------------------------------------
+ * replaces present(): display.frag drawn to the canvas   index.tsx:25-59, shader/display.frag:20-61
+ *          canvas.toDataURL capture                      index.tsx:470-476
+ * Runs the display pass (DoF blur, brightness, gamma 1/2.2) over this rank's rows and copies
+ * local_rows*width*4 bytes of RGBA8 to rgba8_host and, if depth_host != NULL, local_rows*width
+ * floats of hit depth (fp32, latest sample).  Blocking. */
+rmb_status rmb_present(rmb_ctx* ctx, rmb_fb* fb, float brightness, uint8_t* rgba8_host, float* depth_host);
+/* display pass only; the RGBA8 result stays in device memory (rmb_fb_device_ptr(fb, 4)) */
+rmb_status rmb_present_device(rmb_ctx* ctx, rmb_fb* fb, float brightness);
+
+/* ---- inspection (tests, benchmarks) --------------------------------------------------------- */
+/* which: 0 colour (float4), 1 normal+dofRadius (4 x binary16), 2 albedo+depth (4 x binary16),
+ *        3 depth (float), 4 RGBA8 of the last present */
+void* rmb_fb_device_ptr(rmb_fb* fb, int which);
+size_t rmb_fb_plane_bytes(rmb_fb* fb, int which);
+rmb_status rmb_fb_read(rmb_ctx* ctx, rmb_fb* fb, int which, void* host, size_t bytes);
+rmb_status rmb_fb_write(rmb_ctx* ctx, rmb_fb* fb, int which, const void* host, size_t bytes);
+/* out[0] = SDF evaluations executed, out[1] = pixel-samples rendered, since the last reset */
+rmb_status rmb_counters_read(rmb_ctx* ctx, uint64_t out[2], int reset);
+/* evaluates the scene's sdf() and material functions at n points: in n*3 floats, out n*17 floats
+ * (diffuse rgb, specular rgb, roughness, subsurface, subsurfaceColor rgb, IOR, emission rgb, sdf, 0) */
+rmb_status rmb_probe(rmb_ctx* ctx, rmb_program* prog, const float* points_xyz, int n, float* out17);
+/* Lowering + NVRTC compile for sm_100a without touching a GPU (build checks, offline SASS
+ * inspection).  cubin_out/source_out may be NULL. */
+rmb_status rmb_compile_only(const char* scene_glsl, size_t scene_len, int flavour, const rmb_spec_uniform* spec,
+                            int n_spec, char* infolog, size_t infolog_cap, void* cubin_out, size_t cubin_cap,
+                            size_t* cubin_bytes, char* source_out, size_t source_cap);
+/* pinned host memory for the caller's readback buffers */
+void* rmb_host_alloc(size_t bytes);
+void rmb_host_free(void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RMB_H_ */

@@ -1,0 +1,106 @@
+"""ctypes binding of libraymarch_b200.so (C ABI: include/rmb.h).
+
+The library is built in-tree by ``__graft_entry__.build()`` / ``csrc/Makefile``.  There is no
+fallback: if the shared object is missing, importing this module raises, and every rendering
+entry point fails loudly when no CUDA device is present.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+_HERE = Path(__file__).resolve().parent
+LIB_PATH = _HERE / "libraymarch_b200.so"
+
+RMB_OK, RMB_ERR_FRAGMENT, RMB_ERR_PROGRAM, RMB_ERR_GENERAL, RMB_ERR_INVALID = range(5)
+FLAVOUR_EXACT, FLAVOUR_FAST = 0, 1
+UNIFORM_F, UNIFORM_I, UNIFORM_UI = 0, 1, 2
+
+# every symbol include/rmb.h declares; tests check that the library exports all of them
+EXPORTED_SYMBOLS = [
+    "rmb_abi_version", "rmb_ctx_create", "rmb_ctx_destroy", "rmb_last_error", "rmb_ctx_stream", "rmb_sync",
+    "rmb_program_get", "rmb_program_source", "rmb_program_kernel_attr", "rmb_uniform_set", "rmb_uniform_set_array",
+    "rmb_uniform_matrix4", "rmb_fb_acquire", "rmb_fb_release", "rmb_fb_local_rows", "rmb_fb_global_row",
+    "rmb_render_sample", "rmb_present", "rmb_present_device", "rmb_fb_device_ptr", "rmb_fb_plane_bytes",
+    "rmb_fb_read", "rmb_fb_write", "rmb_counters_read", "rmb_probe", "rmb_compile_only", "rmb_host_alloc",
+    "rmb_host_free",
+]
+
+
+class SpecData(C.Union):
+    _fields_ = [("f", C.c_float * 4), ("i", C.c_int32 * 4), ("u", C.c_uint32 * 4)]
+
+
+class SpecUniform(C.Structure):
+    _fields_ = [("name", C.c_char_p), ("type", C.c_int), ("count", C.c_int), ("data", SpecData)]
+
+
+def _load() -> C.CDLL:
+    if not LIB_PATH.exists():
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(or `make -C raymarching_engine_b200/csrc`). There is no CPU fallback."
+        )
+    lib = C.CDLL(os.fspath(LIB_PATH))
+    vp, cp, i, sz, f = C.c_void_p, C.c_char_p, C.c_int, C.c_size_t, C.c_float
+    proto = {
+        "rmb_abi_version": (i, []),
+        "rmb_ctx_create": (vp, [i, i, i, i]),
+        "rmb_ctx_destroy": (None, [vp]),
+        "rmb_last_error": (cp, [vp]),
+        "rmb_ctx_stream": (vp, [vp]),
+        "rmb_sync": (i, [vp]),
+        "rmb_program_get": (i, [vp, cp, sz, i, C.POINTER(SpecUniform), i, C.POINTER(vp), cp, cp, sz]),
+        "rmb_program_source": (cp, [vp]),
+        "rmb_program_kernel_attr": (i, [vp, i, C.POINTER(i), C.POINTER(i)]),
+        "rmb_uniform_set": (i, [vp, cp, i, i, vp]),
+        "rmb_uniform_set_array": (i, [vp, cp, i, i, i, vp]),
+        "rmb_uniform_matrix4": (i, [vp, cp, C.POINTER(f)]),
+        "rmb_fb_acquire": (vp, [vp, i, i, C.c_int64]),
+        "rmb_fb_release": (None, [vp, i, i, C.c_int64]),
+        "rmb_fb_local_rows": (i, [vp]),
+        "rmb_fb_global_row": (i, [vp, i]),
+        "rmb_render_sample": (i, [vp, vp, vp, i, i, i, i]),
+        "rmb_present": (i, [vp, vp, f, vp, vp]),
+        "rmb_present_device": (i, [vp, vp, f]),
+        "rmb_fb_device_ptr": (vp, [vp, i]),
+        "rmb_fb_plane_bytes": (sz, [vp, i]),
+        "rmb_fb_read": (i, [vp, vp, i, vp, sz]),
+        "rmb_fb_write": (i, [vp, vp, i, vp, sz]),
+        "rmb_counters_read": (i, [vp, C.POINTER(C.c_uint64), i]),
+        "rmb_probe": (i, [vp, vp, vp, i, vp]),
+        "rmb_compile_only": (i, [cp, sz, i, C.POINTER(SpecUniform), i, cp, sz, vp, sz, C.POINTER(sz), cp, sz]),
+        "rmb_host_alloc": (vp, [sz]),
+        "rmb_host_free": (None, [vp]),
+    }
+    for name, (res, args) in proto.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    if lib.rmb_abi_version() != 1:
+        raise ImportError("libraymarch_b200.so ABI version mismatch")
+    return lib
+
+
+lib = _load()
+
+
+def make_spec_array(spec: dict | None):
+    """dict name -> UniformData-like (type 'f'|'i'|'ui', data sequence)  ->  (ctypes array, n)"""
+    if not spec:
+        return None, 0
+    arr = (SpecUniform * len(spec))()
+    for k, (name, ud) in enumerate(sorted(spec.items())):
+        arr[k].name = name.encode()
+        t = {"f": UNIFORM_F, "i": UNIFORM_I, "ui": UNIFORM_UI}[ud.type]
+        arr[k].type = t
+        arr[k].count = ud.count
+        for j, v in enumerate(ud.data):
+            if t == UNIFORM_F:
+                arr[k].data.f[j] = float(v)
+            elif t == UNIFORM_I:
+                arr[k].data.i[j] = int(v)
+            else:
+                arr[k].data.u[j] = int(v)
+    return arr, len(spec)

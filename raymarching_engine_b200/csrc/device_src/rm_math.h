@@ -1,0 +1,373 @@
+// rm_math.h -- deterministic transcendental functions shared by the CUDA device code
+// (NVRTC, sm_100a) and the host-side parity oracle (g++, -ffp-contract=off -mfma).
+//
+// Why this exists (hard part H1): the reference's RNG is
+//   gold_noise = fract(tan(distance(xy*PHI, xy)*seed)*xy.x)      raymarcher.frag:46-49
+// which amplifies a 1-ULP change of tan() into a wholesale change of the sample.  GLSL ES 3.00
+// leaves the precision of tan/sin/cos/log/pow/exp implementation-defined, so a parity
+// check is only meaningful when kernel and oracle evaluate *the same* function.  Every
+// function here is built exclusively from IEEE-754 binary64 operations that are correctly
+// rounded on both x86-64 and sm_100 (add, mul, div, sqrt, fma, rint, int<->fp conversion,
+// bit casts), with explicit fma() where fusion is wanted and no reliance on compiler
+// contraction.  Identical source  =>  bit-identical float results on both sides.
+//
+// All functions take/return binary32 and evaluate in binary64; the results are within
+// a fraction of an ULP of the correctly rounded value for arguments in the ranges GLSL
+// code uses (|x| < 1e9 for the trigonometric family), deterministic everywhere else.
+#ifndef RM_MATH_H_
+#define RM_MATH_H_
+
+// Under nvcc/NVRTC every function is __device__-only (the product has no host arithmetic);
+// under g++ (the oracle) they are plain inline host functions.
+#if defined(__CUDACC_RTC__) || defined(__CUDACC__)
+#define RM_DEVICE_CODE 1
+#define RM_HD __device__ __forceinline__
+#else
+#define RM_DEVICE_CODE 0
+#define RM_HD inline
+#include <cstring>
+#include <cmath>
+#endif
+
+namespace rmx {
+
+// ---------------------------------------------------------------- bit casts / primitives
+#if RM_DEVICE_CODE
+RM_HD long long d2ll(double x) { return __double_as_longlong(x); }
+RM_HD double ll2d(long long x) { return __longlong_as_double(x); }
+RM_HD int f2i(float x) { return __float_as_int(x); }
+RM_HD float i2f(int x) { return __int_as_float(x); }
+RM_HD double dfma(double a, double b, double c) { return fma(a, b, c); }
+RM_HD double drint(double x) { return rint(x); }
+RM_HD double dfloor(double x) { return floor(x); }
+RM_HD double dsqrt(double x) { return sqrt(x); }
+RM_HD double dabs(double x) { return fabs(x); }
+#else
+RM_HD long long d2ll(double x) { long long r; memcpy(&r, &x, 8); return r; }
+RM_HD double ll2d(long long x) { double r; memcpy(&r, &x, 8); return r; }
+RM_HD int f2i(float x) { int r; memcpy(&r, &x, 4); return r; }
+RM_HD float i2f(int x) { float r; memcpy(&r, &x, 4); return r; }
+RM_HD double dfma(double a, double b, double c) { return __builtin_fma(a, b, c); }
+RM_HD double drint(double x) { return __builtin_rint(x); }   // round-to-nearest-even mode assumed
+RM_HD double dfloor(double x) { return __builtin_floor(x); }
+RM_HD double dsqrt(double x) { return __builtin_sqrt(x); }
+RM_HD double dabs(double x) { return __builtin_fabs(x); }
+#endif
+
+RM_HD bool f_isnan(float x) { return (f2i(x) & 0x7fffffff) > 0x7f800000; }
+RM_HD bool f_isinf(float x) { return (f2i(x) & 0x7fffffff) == 0x7f800000; }
+RM_HD bool d_isnan(double x) { return (d2ll(x) & 0x7fffffffffffffffLL) > 0x7ff0000000000000LL; }
+RM_HD float f_nan() { return i2f(0x7fffffff); }
+RM_HD float f_inf() { return i2f(0x7f800000); }
+
+// ---------------------------------------------------------------- trigonometric kernels
+// Reduction x = k*(pi/2) + r, |r| <= pi/4, three-term Cody-Waite with fma (constants are the
+// classic split of pi/2 into 33-bit pieces).  k is returned modulo 4 in *quadrant.
+RM_HD double trig_reduce(double x, int* quadrant) {
+    const double TWO_OVER_PI = 6.36619772367581382433e-01;
+    const double PIO2_1 = 1.57079632673412561417e+00;   // first 33 bits of pi/2
+    const double PIO2_2 = 6.07710050630396597660e-11;   // next 33 bits
+    const double PIO2_2T = 2.02226624879595063154e-21;  // remainder
+    double k = drint(x * TWO_OVER_PI);
+    double r = dfma(-k, PIO2_1, x);
+    r = dfma(-k, PIO2_2, r);
+    r = dfma(-k, PIO2_2T, r);
+    double q = dfma(-4.0, dfloor(k * 0.25), k);         // exact: k mod 4 in {0,1,2,3}
+    *quadrant = (int)q;
+    return r;
+}
+
+// sin(r), |r| <= pi/4  (odd minimax polynomial, degree 13)
+RM_HD double ksin(double r) {
+    const double S1 = -1.66666666666666324348e-01, S2 = 8.33333333332248946124e-03,
+                 S3 = -1.98412698298579493134e-04, S4 = 2.75573137070700676789e-06,
+                 S5 = -2.50507602534068634195e-08, S6 = 1.58969099521155010221e-10;
+    double z = r * r;
+    double p = dfma(z, S6, S5);
+    p = dfma(z, p, S4);
+    p = dfma(z, p, S3);
+    p = dfma(z, p, S2);
+    p = dfma(z, p, S1);
+    return dfma(r * z, p, r);
+}
+
+// cos(r), |r| <= pi/4  (even minimax polynomial, degree 14)
+RM_HD double kcos(double r) {
+    const double C1 = 4.16666666666666019037e-02, C2 = -1.38888888888741095749e-03,
+                 C3 = 2.48015872894767294178e-05, C4 = -2.75573143513906633035e-07,
+                 C5 = 2.08757232129817482790e-09, C6 = -1.13596475577881948265e-11;
+    double z = r * r;
+    double p = dfma(z, C6, C5);
+    p = dfma(z, p, C4);
+    p = dfma(z, p, C3);
+    p = dfma(z, p, C2);
+    p = dfma(z, p, C1);
+    return dfma(z * z, p, dfma(z, -0.5, 1.0));
+}
+
+RM_HD float sin_f(float x) {
+    if (f_isnan(x) || f_isinf(x)) return f_nan();
+    int q;
+    double r = trig_reduce((double)x, &q);
+    double s = (q & 1) ? kcos(r) : ksin(r);
+    if (q & 2) s = -s;
+    if (x == 0.0f) return x;  // keep signed zero
+    return (float)s;
+}
+
+RM_HD float cos_f(float x) {
+    if (f_isnan(x) || f_isinf(x)) return f_nan();
+    int q;
+    double r = trig_reduce((double)x, &q);
+    double c = (q & 1) ? ksin(r) : kcos(r);
+    if (((q + 1) & 2) != 0) c = -c;
+    return (float)c;
+}
+
+RM_HD float tan_f(float x) {
+    if (f_isnan(x) || f_isinf(x)) return f_nan();
+    if (x == 0.0f) return x;
+    int q;
+    double r = trig_reduce((double)x, &q);
+    double s = ksin(r), c = kcos(r);
+    double t = (q & 1) ? (-c / s) : (s / c);
+    return (float)t;
+}
+
+// ---------------------------------------------------------------- log2 / exp2 in binary64
+// log2(x) for finite x > 0 (denormal floats promoted to double are normal doubles).
+RM_HD double dlog2_pos(double x) {
+    long long b = d2ll(x);
+    int e = (int)((b >> 52) & 0x7ff) - 1023;
+    long long mb = (b & 0x000fffffffffffffLL) | 0x3ff0000000000000LL;
+    double m = ll2d(mb);                                  // [1,2)
+    if (m > 1.41421356237309514547) { m = m * 0.5; e += 1; }
+    double f = m - 1.0;                                   // [-0.2929, 0.4142]
+    double s = f / (2.0 + f);                             // |s| <= 0.1716
+    double z = s * s;
+    // atanh series: ln(m) = 2s(1 + z/3 + z^2/5 + ... ), 12 terms => < 1e-18 truncation
+    double p = 1.0 / 25.0;
+    p = dfma(z, p, 1.0 / 23.0);
+    p = dfma(z, p, 1.0 / 21.0);
+    p = dfma(z, p, 1.0 / 19.0);
+    p = dfma(z, p, 1.0 / 17.0);
+    p = dfma(z, p, 1.0 / 15.0);
+    p = dfma(z, p, 1.0 / 13.0);
+    p = dfma(z, p, 1.0 / 11.0);
+    p = dfma(z, p, 1.0 / 9.0);
+    p = dfma(z, p, 1.0 / 7.0);
+    p = dfma(z, p, 1.0 / 5.0);
+    p = dfma(z, p, 1.0 / 3.0);
+    p = dfma(z, p, 1.0);
+    double lnm = 2.0 * s * p;
+    const double INV_LN2 = 1.44269504088896338700e+00;
+    return dfma(lnm, INV_LN2, (double)e);
+}
+
+// 2^t for any double t; result is a double that converts to the wanted float
+// (overflow -> +inf, underflow -> denormal/0 through the final conversion).
+RM_HD double dexp2(double t) {
+    if (d_isnan(t)) return t;
+    if (t > 1000.0) t = 1000.0;
+    if (t < -1000.0) t = -1000.0;
+    double n = drint(t);
+    double f = (t - n) * 6.93147180559945286227e-01;      // f*ln2, |f| <= 0.3466
+    // exp(f) Taylor to degree 14 (0.3466^15/15! ~ 1e-19)
+    double p = 1.0 / 87178291200.0;
+    p = dfma(f, p, 1.0 / 6227020800.0);
+    p = dfma(f, p, 1.0 / 479001600.0);
+    p = dfma(f, p, 1.0 / 39916800.0);
+    p = dfma(f, p, 1.0 / 3628800.0);
+    p = dfma(f, p, 1.0 / 362880.0);
+    p = dfma(f, p, 1.0 / 40320.0);
+    p = dfma(f, p, 1.0 / 5040.0);
+    p = dfma(f, p, 1.0 / 720.0);
+    p = dfma(f, p, 1.0 / 120.0);
+    p = dfma(f, p, 1.0 / 24.0);
+    p = dfma(f, p, 1.0 / 6.0);
+    p = dfma(f, p, 0.5);
+    p = dfma(f, p, 1.0);
+    p = dfma(f, p, 1.0);
+    long long sb = ((long long)((int)n + 1023)) << 52;    // |n| <= 1000 so exponent is in range
+    return p * ll2d(sb);
+}
+
+RM_HD float log2_f(float x) {
+    if (f_isnan(x) || x < 0.0f) return f_nan();
+    if (x == 0.0f) return -f_inf();
+    if (f_isinf(x)) return x;
+    return (float)dlog2_pos((double)x);
+}
+
+RM_HD float log_f(float x) {
+    if (f_isnan(x) || x < 0.0f) return f_nan();
+    if (x == 0.0f) return -f_inf();
+    if (f_isinf(x)) return x;
+    return (float)(dlog2_pos((double)x) * 6.93147180559945286227e-01);
+}
+
+RM_HD float exp2_f(float x) { return (float)dexp2((double)x); }
+
+RM_HD float exp_f(float x) { return (float)dexp2((double)x * 1.44269504088896338700e+00); }
+
+// pow(x, y).  GLSL ES 3.00 leaves x < 0 undefined; the reference relies on pow(negative, 2.0)
+// being a square (schlick(), raymarcher.frag:173, with n1 < n2), which is what GPU compilers
+// deliver by strength-reducing constant integer exponents.  Pinned: C99 powf semantics - a
+// negative base with an integral exponent gives +-|x|^y, otherwise NaN; pow(x,0)=1, pow(0,y>0)=0.
+RM_HD float pow_f(float x, float y) {
+    if (f_isnan(x) || f_isnan(y)) return f_nan();
+    if (y == 0.0f) return 1.0f;
+    bool negate = false;
+    if (x < 0.0f) {
+        double yd = (double)y;
+        if (f_isinf(y)) { x = -x; }
+        else {
+            if (yd != drint(yd)) return f_nan();
+            double h = yd * 0.5;
+            negate = (h != drint(h)) && (dabs(yd) < 16777216.0);   // odd integer exponent
+            x = -x;
+        }
+    }
+    float r;
+    if (x == 0.0f) r = (y > 0.0f) ? 0.0f : f_inf();
+    else if (f_isinf(x)) r = (y > 0.0f) ? f_inf() : 0.0f;
+    else if (x == 1.0f) r = 1.0f;
+    else if (f_isinf(y)) {
+        bool grow = (x > 1.0f) == (y > 0.0f);
+        r = grow ? f_inf() : 0.0f;
+    } else r = (float)dexp2((double)y * dlog2_pos((double)x));
+    return negate ? -r : r;
+}
+
+// ---------------------------------------------------------------- inverse trigonometric
+// atan for a double argument, result in (-pi/2, pi/2).
+RM_HD double datan(double x) {
+    const double PIO2 = 1.57079632679489655800e+00;
+    bool neg = x < 0.0;
+    double a = neg ? -x : x;
+    bool inv = a > 1.0;
+    if (inv) a = 1.0 / a;
+    // two argument halvings: atan(a) = 2 atan(a / (1 + sqrt(1 + a^2)))  -> |a| <= 0.1990
+    a = a / (1.0 + dsqrt(dfma(a, a, 1.0)));
+    a = a / (1.0 + dsqrt(dfma(a, a, 1.0)));
+    double z = a * a;
+    double p = -1.0 / 23.0;
+    p = dfma(z, p, 1.0 / 21.0);
+    p = dfma(z, p, -1.0 / 19.0);
+    p = dfma(z, p, 1.0 / 17.0);
+    p = dfma(z, p, -1.0 / 15.0);
+    p = dfma(z, p, 1.0 / 13.0);
+    p = dfma(z, p, -1.0 / 11.0);
+    p = dfma(z, p, 1.0 / 9.0);
+    p = dfma(z, p, -1.0 / 7.0);
+    p = dfma(z, p, 1.0 / 5.0);
+    p = dfma(z, p, -1.0 / 3.0);
+    p = dfma(z, p, 1.0);
+    double r = 4.0 * a * p;
+    if (inv) r = PIO2 - r;
+    return neg ? -r : r;
+}
+
+RM_HD double datan2(double y, double x) {
+    const double PI = 3.14159265358979311600e+00;
+    const double PIO2 = 1.57079632679489655800e+00;
+    if (d_isnan(x) || d_isnan(y)) return x + y;
+    if (x == 0.0) {
+        if (y == 0.0) return 0.0;
+        return y > 0.0 ? PIO2 : -PIO2;
+    }
+    double ax = dabs(x), ay = dabs(y);
+    double r;
+    if (ax >= ay) r = datan(ay / ax); else r = PIO2 - datan(ax / ay);
+    if (x < 0.0) r = PI - r;
+    return y < 0.0 ? -r : r;
+}
+
+RM_HD float atan_f(float x) {
+    if (f_isnan(x)) return f_nan();
+    if (f_isinf(x)) return x > 0.0f ? 1.57079637f : -1.57079637f;
+    if (x == 0.0f) return x;
+    return (float)datan((double)x);
+}
+RM_HD float atan2_f(float y, float x) {
+    if (f_isnan(x) || f_isnan(y)) return f_nan();
+    if (f_isinf(x) || f_isinf(y)) {
+        // map infinities to unit steps: (inf,inf) -> 45 degree family, one-sided -> axis
+        double dx = f_isinf(x) ? (x > 0.0f ? 1.0 : -1.0) : 0.0;
+        double dy = f_isinf(y) ? (y > 0.0f ? 1.0 : -1.0) : 0.0;
+        if (dy == 0.0) {
+            double r = dx > 0.0 ? 0.0 : 3.14159265358979311600e+00;
+            return (float)(y < 0.0f ? -r : r);
+        }
+        return (float)datan2(dy, dx);
+    }
+    return (float)datan2((double)y, (double)x);
+}
+RM_HD float asin_f(float x) {
+    if (f_isnan(x) || x > 1.0f || x < -1.0f) return f_nan();
+    if (x == 0.0f) return x;
+    double d = (double)x;
+    return (float)datan2(d, dsqrt((1.0 - d) * (1.0 + d)));
+}
+RM_HD float acos_f(float x) {
+    if (f_isnan(x) || x > 1.0f || x < -1.0f) return f_nan();
+    double d = (double)x;
+    return (float)datan2(dsqrt((1.0 - d) * (1.0 + d)), d);
+}
+
+// ---------------------------------------------------------------- hyperbolic family
+RM_HD double dexp(double x) { return dexp2(x * 1.44269504088896338700e+00); }
+RM_HD double dlog(double x) { return dlog2_pos(x) * 6.93147180559945286227e-01; }
+
+RM_HD float sinh_f(float x) {
+    if (f_isnan(x)) return f_nan();
+    if (x == 0.0f || f_isinf(x)) return x;
+    double d = (double)x;
+    if (dabs(d) < 1e-4) return (float)dfma(d * d * d, 1.0 / 6.0, d);
+    if (dabs(d) > 700.0) return d > 0.0 ? f_inf() : -f_inf();
+    double e = dexp(d);
+    return (float)(0.5 * (e - 1.0 / e));
+}
+RM_HD float cosh_f(float x) {
+    if (f_isnan(x)) return f_nan();
+    if (f_isinf(x)) return f_inf();
+    double d = dabs((double)x);
+    if (d > 700.0) return f_inf();
+    double e = dexp(d);
+    return (float)(0.5 * (e + 1.0 / e));
+}
+RM_HD float tanh_f(float x) {
+    if (f_isnan(x)) return f_nan();
+    if (x == 0.0f) return x;
+    double d = (double)x;
+    if (dabs(d) > 20.0) return d > 0.0 ? 1.0f : -1.0f;
+    if (dabs(d) < 1e-4) return (float)dfma(d * d * d, -1.0 / 3.0, d);
+    double e = dexp(2.0 * d);
+    return (float)((e - 1.0) / (e + 1.0));
+}
+RM_HD float asinh_f(float x) {
+    if (f_isnan(x)) return f_nan();
+    if (x == 0.0f || f_isinf(x)) return x;
+    double d = dabs((double)x);
+    double r = (d < 1e-4) ? dfma(d * d * d, -1.0 / 6.0, d) : dlog(d + dsqrt(dfma(d, d, 1.0)));
+    return (float)(x < 0.0f ? -r : r);
+}
+RM_HD float acosh_f(float x) {
+    if (f_isnan(x) || x < 1.0f) return f_nan();
+    if (f_isinf(x)) return x;
+    double d = (double)x;
+    return (float)dlog(d + dsqrt((d - 1.0) * (d + 1.0)));
+}
+RM_HD float atanh_f(float x) {
+    if (f_isnan(x) || x > 1.0f || x < -1.0f) return f_nan();
+    if (x == 0.0f) return x;
+    if (x == 1.0f) return f_inf();
+    if (x == -1.0f) return -f_inf();
+    double d = (double)x;
+    if (dabs(d) < 1e-4) return (float)dfma(d * d * d, 1.0 / 3.0, d);
+    return (float)(0.5 * dlog((1.0 + d) / (1.0 - d)));
+}
+
+}  // namespace rmx
+
+#endif  // RM_MATH_H_

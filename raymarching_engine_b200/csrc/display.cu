@@ -1,0 +1,94 @@
+// display.cu -- the present pass as a CUDA kernel (statically compiled for sm_100a).
+//
+// Restates /root/reference/client/public/shader/display.frag:20-61 as driven by
+// /root/reference/client/src/index.tsx:25-59: per pixel a variable-radius Gaussian blur of the
+// colour accumulator (radius from the accumulated depth-of-field radius), times brightness,
+// gamma 1/2.2, alpha 1, converted to RGBA8.  Textures are NEAREST + REPEAT
+// (/root/reference/client/src/renderer/LoadRenderJobContext.tsx:43-48).
+//
+// Arithmetic uses the exact policy of glsl_rt.h (single IEEE operations ptxas cannot fuse and
+// the shared rm_math.h exp/pow) so the bytes are identical to the CPU oracle's.
+//
+// Layout: one thread per pixel, consecutive threads along x; each thread writes one uchar4
+// (a warp writes one full 128-byte line).  Rows are this rank's LOCAL rows; the texcoord uses the
+// global row.  The blur reads neighbours from the local buffer, which is only correct when this
+// rank owns the whole frame (n_ranks == 1) or the blur radius is 0 (preview mode);
+// the host gathers the colour plane to one rank before presenting a blurred multi-GPU frame.
+#include <cuda_runtime.h>
+
+#define GLSL_NS xg
+#define GLSL_FAST 0
+#include "device_src/glsl_rt.h"
+
+namespace xg {
+namespace disp {
+
+__device__ __forceinline__ float h2f(unsigned short h) {
+    float f;
+    asm("{ .reg .b16 t; mov.b16 t, %1; cvt.f32.f16 %0, t; }" : "=f"(f) : "h"(h));
+    return f;
+}
+
+__global__ void __launch_bounds__(256) rm_display_kernel(const float4* __restrict__ color, const ushort4* __restrict__ nd,
+                                                         uchar4* __restrict__ out, int W, int localRows, int H,
+                                                         int tileRows, int nRanks, int rank, float brightness) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int ly = blockIdx.y;
+    if (x >= W || ly >= localRows) return;
+    const int t = ly / tileRows;
+    const int gy = (t * nRanks + rank) * tileRows + (ly - t * tileRows);
+    const size_t idx = (size_t)ly * (size_t)W + (size_t)x;
+    const vec2 texcoord(g_div(g_add((float)x, 0.5f), (float)W), g_div(g_add((float)gy, 0.5f), (float)H));
+    const float PI_D = 3.1415926535f;                                    // display.frag:9
+    const float ndw = g_mul(h2f(nd[idx].w), brightness);                  // display.frag:18
+    const float kernelSize = clamp(g_mul(ndw, 200.0f), 0.0f, 16.0f);     // :20
+    vec4 avg(0.0f);
+    float sampleCount = 0.0f;
+    const float sigma = g_mul(max(kernelSize, 1.0f), 0.3f);
+    const float norm = g_div(1.0f, g_mul(g_mul(g_mul(2.0f, PI_D), sigma), sigma));
+    const float twoSigma2 = g_mul(g_mul(2.0f, sigma), sigma);
+    for (float y = -kernelSize; y <= kernelSize; y = g_add(y, 1.0f)) {   // :42-50
+        for (float xo = -kernelSize; xo <= kernelSize; xo = g_add(xo, 1.0f)) {
+            const vec2 offset(xo, y);
+            const vec2 texOffset = offset / vec2((float)W, (float)H);
+            const float factor = g_mul(norm, exp(-g_div(dot(offset, offset), twoSigma2)));
+            sampleCount = g_add(sampleCount, factor);
+            const vec2 uv = texcoord + texOffset;
+            // NEAREST + REPEAT: texel = floor(uv * size) mod size
+            long long i = (long long)floor(g_mul(uv.x, (float)W));
+            long long j = (long long)floor(g_mul(uv.y, (float)H));
+            i %= W; if (i < 0) i += W;
+            j %= H; if (j < 0) j += H;
+            // global row j -> local row (identity when this rank owns every row)
+            long long lj = j;
+            if (nRanks > 1) {
+                const long long tj = j / tileRows;
+                lj = (tj / nRanks) * tileRows + (j - tj * tileRows);
+                if (tj % nRanks != rank) lj = ly;   // not resident here (see header note)
+            }
+            const float4 c = color[(size_t)lj * (size_t)W + (size_t)i];
+            avg += vec4(c.x, c.y, c.z, c.w) * factor;
+        }
+    }
+    avg /= sampleCount;
+    const vec4 frag = pow(vec4(vec3(avg.x, avg.y, avg.z) * brightness, 1.0f), vec4(g_div(1.0f, 2.2f)));   // :54
+    unsigned char b[4];
+    for (int cpt = 0; cpt < 4; cpt++) {
+        float v = frag[cpt];
+        if (isnan(v)) v = 0.0f;
+        v = clamp(v, 0.0f, 1.0f);
+        b[cpt] = (unsigned char)(int)floor(g_add(g_mul(v, 255.0f), 0.5f));
+    }
+    out[idx] = make_uchar4(b[0], b[1], b[2], b[3]);
+}
+
+}  // namespace disp
+}  // namespace xg
+
+extern "C" cudaError_t rmb_launch_display(const void* color, const void* nd, void* rgba8, int W, int local_rows, int H,
+                                          int tile_rows, int n_ranks, int rank, float brightness, cudaStream_t stream) {
+    dim3 block(256, 1, 1), grid((unsigned)((W + 255) / 256), (unsigned)local_rows, 1);
+    xg::disp::rm_display_kernel<<<grid, block, 0, stream>>>((const float4*)color, (const ushort4*)nd, (uchar4*)rgba8, W,
+                                                            local_rows, H, tile_rows, n_ranks, rank, brightness);
+    return cudaGetLastError();
+}

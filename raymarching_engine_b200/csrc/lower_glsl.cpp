@@ -1,0 +1,393 @@
+// lower_glsl.cpp -- token-level lowering of a GLSL ES 3.00 scene to C++ that compiles against
+// device_src/glsl_rt.h inside `struct Frag`.  See lower_glsl.h.
+//
+// What the lowering does (everything else in GLSL's expression/statement syntax is already
+// valid C++ given the vector types, swizzle proxies and built-ins of glsl_rt.h):
+//   * comments are blanked, line structure is preserved (diagnostics keep scene line numbers);
+//   * `uniform T name[N];` declarations at global scope are collected and removed;
+//   * floating literals get an `f` suffix (GLSL `1.0` is fp32, C++ `1.0` is double);
+//   * `precision ...;` statements, precision qualifiers and `layout(...)` are dropped;
+//   * parameter qualifiers: `in` is dropped, `out`/`inout` turn the parameter into a reference;
+//   * identifiers that are C++ keywords but legal GLSL names are renamed (`not` -> `not_`);
+//   * `#version` / `#extension` lines are dropped, other preprocessor lines pass through;
+//   * functions defined at global scope are recorded (for default-function injection);
+//   * purity analysis: a scene that declares mutable globals or touches the RNG state
+//     (`seed`, uniformSample, ...) may not use the fixed-point early exit.
+#include "lower_glsl.h"
+
+#include <cctype>
+#include <cstring>
+#include <map>
+
+namespace rmb {
+
+namespace {
+
+enum Kind { kIdent, kNumber, kPunct, kPP };
+
+struct Token {
+    Kind kind;
+    std::string text;
+    std::string ws;   // whitespace (incl. newlines and blanked comments) preceding the token
+    int line;
+    bool drop = false;
+};
+
+bool is_ident_start(char c) { return std::isalpha((unsigned char)c) || c == '_'; }
+bool is_ident_char(char c) { return std::isalnum((unsigned char)c) || c == '_'; }
+
+// Splits the source into tokens; comments become whitespace (newlines kept).
+std::vector<Token> tokenize(const std::string& s, std::string* trailing_ws) {
+    std::vector<Token> out;
+    std::string ws;
+    int line = 1;
+    size_t i = 0, n = s.size();
+    bool line_start = true;
+    while (i < n) {
+        char c = s[i];
+        if (c == '\n') { ws += '\n'; line++; i++; line_start = true; continue; }
+        if (c == ' ' || c == '\t' || c == '\r' || c == '\f' || c == '\v') { ws += (c == '\r' ? ' ' : c); i++; continue; }
+        if (c == '/' && i + 1 < n && s[i + 1] == '/') {
+            while (i < n && s[i] != '\n') i++;
+            continue;
+        }
+        if (c == '/' && i + 1 < n && s[i + 1] == '*') {
+            i += 2;
+            while (i < n && !(s[i] == '*' && i + 1 < n && s[i + 1] == '/')) {
+                if (s[i] == '\n') { ws += '\n'; line++; }
+                i++;
+            }
+            i = (i + 2 <= n) ? i + 2 : n;
+            ws += ' ';
+            continue;
+        }
+        Token t;
+        t.line = line;
+        t.ws = ws;
+        ws.clear();
+        if (c == '#' && line_start) {
+            // whole preprocessor line (with backslash continuations)
+            size_t j = i;
+            while (j < n) {
+                if (s[j] == '\n') {
+                    if (j > 0 && s[j - 1] == '\\') { line++; j++; continue; }
+                    break;
+                }
+                j++;
+            }
+            t.kind = kPP;
+            t.text = s.substr(i, j - i);
+            i = j;
+            out.push_back(t);
+            continue;
+        }
+        line_start = false;
+        if (is_ident_start(c)) {
+            size_t j = i;
+            while (j < n && is_ident_char(s[j])) j++;
+            t.kind = kIdent;
+            t.text = s.substr(i, j - i);
+            i = j;
+        } else if (std::isdigit((unsigned char)c) || (c == '.' && i + 1 < n && std::isdigit((unsigned char)s[i + 1]))) {
+            size_t j = i;
+            bool is_float = false, is_hex = false;
+            if (c == '0' && j + 1 < n && (s[j + 1] == 'x' || s[j + 1] == 'X')) {
+                is_hex = true;
+                j += 2;
+                while (j < n && std::isxdigit((unsigned char)s[j])) j++;
+            } else {
+                while (j < n && std::isdigit((unsigned char)s[j])) j++;
+                if (j < n && s[j] == '.') { is_float = true; j++; while (j < n && std::isdigit((unsigned char)s[j])) j++; }
+                if (j < n && (s[j] == 'e' || s[j] == 'E')) {
+                    size_t k = j + 1;
+                    if (k < n && (s[k] == '+' || s[k] == '-')) k++;
+                    if (k < n && std::isdigit((unsigned char)s[k])) {
+                        is_float = true;
+                        j = k;
+                        while (j < n && std::isdigit((unsigned char)s[j])) j++;
+                    }
+                }
+            }
+            std::string num = s.substr(i, j - i);
+            // suffixes: f/F (float), u/U (unsigned)
+            if (j < n && (s[j] == 'f' || s[j] == 'F') && !is_hex) { is_float = true; j++; }
+            else if (j < n && (s[j] == 'u' || s[j] == 'U')) { num += 'u'; j++; }
+            if (is_float) {
+                // "1." is valid in both languages; make sure the result is an fp32 literal
+                num += 'f';
+            }
+            t.kind = kNumber;
+            t.text = num;
+            i = j;
+        } else {
+            // multi-character operators are kept together only where it matters for pasting
+            static const char* ops[] = {"<<=", ">>=", "++", "--", "+=", "-=", "*=", "/=", "%=", "&=", "|=", "^=",
+                                        "==", "!=", "<=", ">=", "&&", "||", "^^", "<<", ">>", nullptr};
+            t.kind = kPunct;
+            t.text = std::string(1, c);
+            for (int k = 0; ops[k]; k++) {
+                size_t L = strlen(ops[k]);
+                if (s.compare(i, L, ops[k]) == 0) { t.text = ops[k]; break; }
+            }
+            i += t.text.size();
+        }
+        out.push_back(t);
+    }
+    *trailing_ws = ws;
+    return out;
+}
+
+const std::set<std::string>& precision_words() {
+    static const std::set<std::string> s = {"highp", "mediump", "lowp"};
+    return s;
+}
+
+// C++ keywords / alternative tokens that GLSL ES 3.00 does not reserve
+const std::map<std::string, std::string>& renames() {
+    static const std::map<std::string, std::string> m = {
+        {"not", "not_"},           {"and", "and_rmk"},         {"or", "or_rmk"},         {"xor", "xor_rmk"},
+        {"bitand", "bitand_rmk"},  {"bitor", "bitor_rmk"},     {"compl", "compl_rmk"},   {"and_eq", "and_eq_rmk"},
+        {"or_eq", "or_eq_rmk"},    {"xor_eq", "xor_eq_rmk"},   {"not_eq", "not_eq_rmk"}, {"new", "new_rmk"},
+        {"delete", "delete_rmk"},  {"try", "try_rmk"},         {"catch", "catch_rmk"},   {"throw", "throw_rmk"},
+        {"char", "char_rmk"},      {"auto", "auto_rmk"},       {"register", "register_rmk"}, {"explicit", "explicit_rmk"},
+        {"mutable", "mutable_rmk"}, {"friend", "friend_rmk"},  {"virtual", "virtual_rmk"}, {"private", "private_rmk"},
+        {"protected", "protected_rmk"}, {"operator", "operator_rmk"}, {"typename", "typename_rmk"},
+        {"wchar_t", "wchar_t_rmk"}, {"nullptr", "nullptr_rmk"}, {"alignas", "alignas_rmk"}, {"alignof", "alignof_rmk"},
+        {"decltype", "decltype_rmk"}, {"constexpr", "constexpr_rmk"}, {"noexcept", "noexcept_rmk"},
+        {"static_assert", "static_assert_rmk"}, {"thread_local", "thread_local_rmk"}, {"signed", "signed_rmk"},
+        {"char16_t", "char16_t_rmk"}, {"char32_t", "char32_t_rmk"}, {"char8_t", "char8_t_rmk"},
+        {"concept", "concept_rmk"}, {"requires", "requires_rmk"}, {"consteval", "consteval_rmk"},
+        {"constinit", "constinit_rmk"}, {"co_await", "co_await_rmk"}, {"co_return", "co_return_rmk"},
+        {"co_yield", "co_yield_rmk"}, {"reinterpret_cast", "reinterpret_cast_rmk"}, {"static_cast", "static_cast_rmk"},
+        {"dynamic_cast", "dynamic_cast_rmk"}, {"const_cast", "const_cast_rmk"}, {"typeid", "typeid_rmk"},
+        {"asm", "asm_rmk"}, {"export", "export_rmk"}, {"final", "final"}, {"override", "override"},
+    };
+    return m;
+}
+
+const std::set<std::string>& rng_state_words() {
+    static const std::set<std::string> s = {"seed", "uniformSample", "boxMullerTransform", "sphereSample", "circleSample"};
+    return s;
+}
+
+}  // namespace
+
+bool uniform_type_info(const std::string& type, char* base, int* components) {
+    struct E { const char* n; char b; int c; };
+    static const E table[] = {
+        {"float", 'f', 1}, {"vec2", 'f', 2},  {"vec3", 'f', 3},  {"vec4", 'f', 4},  {"int", 'i', 1},   {"ivec2", 'i', 2},
+        {"ivec3", 'i', 3}, {"ivec4", 'i', 4}, {"uint", 'u', 1},  {"uvec2", 'u', 2}, {"uvec3", 'u', 3}, {"uvec4", 'u', 4},
+        {"bool", 'b', 1},  {"bvec2", 'b', 2}, {"bvec3", 'b', 3}, {"bvec4", 'b', 4}, {"mat2", 'f', 4},  {"mat3", 'f', 9},
+        {"mat4", 'f', 16},
+    };
+    for (const E& e : table)
+        if (type == e.n) { *base = e.b; *components = e.c; return true; }
+    return false;
+}
+
+const std::vector<DefaultFunction>& default_material_functions() {
+    // Restated from Validate.tsx:18-51 (the reference appends these GLSL bodies when the scene
+    // does not define the function).
+    static const std::vector<DefaultFunction> v = {
+        {"sceneDiffuseColor",
+         "vec3 sceneDiffuseColor(vec3 position) { if (length(position) > 35.0f) return vec3(0.0f); return vec3(0.6f); }\n"},
+        {"sceneSpecularColor",
+         "vec3 sceneSpecularColor(vec3 position) { if (length(position) > 35.0f) return vec3(0.0f); return vec3(0.6f); }\n"},
+        {"sceneSpecularRoughness", "float sceneSpecularRoughness(vec3 position) { return 0.2f; }\n"},
+        {"sceneSubsurfaceScattering", "float sceneSubsurfaceScattering(vec3 position) { return 11111115.0f; }\n"},
+        {"sceneSubsurfaceScatteringColor",
+         "vec3 sceneSubsurfaceScatteringColor(vec3 position) { if (length(position) > 30.0f) return vec3(1.0f); return vec3(1.0f); }\n"},
+        {"sceneIOR", "float sceneIOR(vec3 position) { return 100.0f; }\n"},
+        {"sceneEmission",
+         "vec3 sceneEmission(vec3 position) { float d = max(normalize(position).y, 0.2f); "
+         "vec3 brightColor = vec3(0.7f, 0.8f, 1.0f) * d * 1.0f; "
+         "return (length(position) > 36.0f) ? (brightColor * 2.00f) : vec3(0.0f); }\n"},
+    };
+    return v;
+}
+
+LowerResult lower_scene(const std::string& glsl) {
+    LowerResult R;
+    std::string trailing;
+    std::vector<Token> T = tokenize(glsl, &trailing);
+    const size_t n = T.size();
+
+    auto fail = [&](int line, const std::string& msg) {
+        R.ok = false;
+        R.error = "ERROR: 0:" + std::to_string(line) + ": " + msg;
+        return R;
+    };
+
+    // ---- pass 1: structural walk at global scope ------------------------------------------
+    int brace = 0, paren = 0;
+    size_t i = 0;
+    // statement_start: index of the first token of the current global-scope declaration
+    bool at_decl_start = true;
+    while (i < n) {
+        Token& t = T[i];
+        if (t.kind == kPP) {
+            // #version / #extension are GLSL-only
+            size_t p = 1;
+            while (p < t.text.size() && (t.text[p] == ' ' || t.text[p] == '\t')) p++;
+            std::string d = t.text.substr(p, 9);
+            if (d.compare(0, 7, "version") == 0 || d.compare(0, 9, "extension") == 0) t.drop = true;
+            i++;
+            continue;
+        }
+        if (t.kind == kIdent) {
+            if (precision_words().count(t.text)) { t.drop = true; i++; continue; }
+            if (t.text == "precision") {
+                // precision <qual> <type> ;
+                size_t j = i;
+                while (j < n && !(T[j].kind == kPunct && T[j].text == ";")) { T[j].drop = true; j++; }
+                if (j < n) T[j].drop = true;
+                i = j + 1;
+                continue;
+            }
+            auto rn = renames().find(t.text);
+            if (rn != renames().end()) t.text = rn->second;
+            if (rng_state_words().count(t.text)) R.pure = false;
+        }
+        if (brace == 0 && paren == 0 && t.kind == kIdent && at_decl_start) {
+            // ---- global-scope declaration ----
+            if (t.text == "layout") {
+                t.drop = true;
+                size_t j = i + 1;
+                if (j < n && T[j].text == "(") {
+                    int d = 0;
+                    while (j < n) {
+                        if (T[j].text == "(") d++;
+                        if (T[j].text == ")") d--;
+                        T[j].drop = true;
+                        j++;
+                        if (d == 0) break;
+                    }
+                }
+                i = j;
+                continue;   // still at declaration start
+            }
+            if (t.text == "uniform") {
+                size_t j = i + 1;
+                t.drop = true;
+                while (j < n && T[j].kind == kIdent && (precision_words().count(T[j].text))) { T[j].drop = true; j++; }
+                if (j >= n || T[j].kind != kIdent) return fail(t.line, "'uniform' : syntax error");
+                std::string type = T[j].text;
+                char b; int c;
+                if (!uniform_type_info(type, &b, &c)) {
+                    if (type.compare(0, 7, "sampler") == 0 || type.compare(0, 8, "isampler") == 0 || type.compare(0, 8, "usampler") == 0)
+                        return fail(T[j].line, "'" + type + "' : sampler uniforms are not available to scene code");
+                    return fail(T[j].line, "'" + type + "' : unsupported uniform type");
+                }
+                T[j].drop = true;
+                j++;
+                for (;;) {
+                    if (j >= n || T[j].kind != kIdent) return fail(t.line, "'uniform' : expected identifier");
+                    UniformDecl u;
+                    u.type = type;
+                    u.name = T[j].text;
+                    u.line = T[j].line;
+                    T[j].drop = true;
+                    j++;
+                    if (j < n && T[j].text == "[") {
+                        T[j].drop = true;
+                        j++;
+                        if (j >= n || T[j].kind != kNumber) return fail(u.line, "'" + u.name + "' : array size must be an integer literal");
+                        u.array_size = std::atoi(T[j].text.c_str());
+                        if (u.array_size <= 0) return fail(u.line, "'" + u.name + "' : array size must be positive");
+                        T[j].drop = true;
+                        j++;
+                        if (j >= n || T[j].text != "]") return fail(u.line, "'" + u.name + "' : expected ']'");
+                        T[j].drop = true;
+                        j++;
+                    }
+                    R.uniforms.push_back(u);
+                    if (j < n && T[j].text == ",") { T[j].drop = true; j++; continue; }
+                    break;
+                }
+                if (j >= n || T[j].text != ";") return fail(t.line, "'uniform' : expected ';'");
+                T[j].drop = true;
+                i = j + 1;
+                continue;
+            }
+            if (t.text == "in" || t.text == "out" || t.text == "inout" || t.text == "flat" || t.text == "smooth" || t.text == "centroid" || t.text == "invariant") {
+                // interface qualifiers make no sense in spliced scene code; treat as plain global
+                t.drop = true;
+                i++;
+                continue;
+            }
+            // function definition / prototype:  [const] type name ( ... ) { | ;
+            size_t j = i;
+            bool is_const = false;
+            if (T[j].text == "const") { is_const = true; j++; }
+            if (T[j].text == "struct") {
+                // struct definition: skip to the matching close brace at this level (members are
+                // plain declarations, valid C++)
+                at_decl_start = false;
+                i++;
+                continue;
+            }
+            if (j + 2 < n && T[j].kind == kIdent && T[j + 1].kind == kIdent && T[j + 2].text == "(") {
+                // find matching ')'
+                size_t k = j + 2;
+                int d = 0;
+                size_t close = 0;
+                while (k < n) {
+                    if (T[k].text == "(") d++;
+                    if (T[k].text == ")") { d--; if (d == 0) { close = k; break; } }
+                    k++;
+                }
+                if (!close) return fail(t.line, "'" + T[j + 1].text + "' : unbalanced parentheses");
+                // parameter qualifiers
+                for (size_t q = j + 3; q < close; q++) {
+                    if (T[q].kind != kIdent) continue;
+                    bool param_start = (q == j + 3) || T[q - 1].text == "," || (T[q - 1].kind == kIdent && (T[q - 1].text == "const" || T[q - 1].drop));
+                    if (!param_start) continue;
+                    if (T[q].text == "in") { T[q].drop = true; }
+                    else if (T[q].text == "out" || T[q].text == "inout") {
+                        T[q].drop = true;
+                        size_t ty = q + 1;
+                        while (ty < close && T[ty].kind == kIdent && precision_words().count(T[ty].text)) ty++;
+                        if (ty < close && T[ty].kind == kIdent) T[ty].text += "&";
+                    }
+                }
+                if (close + 1 < n && T[close + 1].text == "{") R.functions.insert(T[j + 1].text);
+                // `void f(void)` is fine in C++ too
+                at_decl_start = false;
+                i++;
+                continue;
+            }
+            // otherwise a global variable declaration
+            if (!is_const) R.pure = false;
+            at_decl_start = false;
+            i++;
+            continue;
+        }
+        if (t.kind == kPunct) {
+            if (t.text == "{") brace++;
+            else if (t.text == "}") { brace--; if (brace < 0) return fail(t.line, "'}' : syntax error"); if (brace == 0 && paren == 0) at_decl_start = true; }
+            else if (t.text == "(") paren++;
+            else if (t.text == ")") { paren--; if (paren < 0) return fail(t.line, "')' : syntax error"); }
+            else if (t.text == ";" && brace == 0 && paren == 0) at_decl_start = true;
+            else if (t.text == "^^") t.text = "!=";   // logical xor on bools
+        }
+        i++;
+    }
+    if (brace != 0) return fail(n ? T[n - 1].line : 1, "unexpected end of source: unbalanced '{'");
+
+    // ---- emit -------------------------------------------------------------------------------
+    std::string out;
+    out.reserve(glsl.size() + 256);
+    for (const Token& t : T) {
+        out += t.ws;
+        if (t.drop) continue;
+        // separate tokens that would otherwise paste after a dropped neighbour
+        if (!out.empty() && is_ident_char(out.back()) && !t.text.empty() && is_ident_char(t.text[0]) && t.ws.empty()) out += ' ';
+        out += t.text;
+    }
+    out += trailing;
+    R.body = out;
+    R.ok = true;
+    return R;
+}
+
+}  // namespace rmb

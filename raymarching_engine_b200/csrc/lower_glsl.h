@@ -1,0 +1,42 @@
+// lower_glsl.h -- GLSL ES 3.00 scene source -> CUDA C++ member declarations for struct Frag
+// (device_src/raymarch_kernel.cuh).  Replaces the role the browser's GLSL compiler plays for
+// the scene splice at /root/reference/client/public/shader/raymarcher.frag:146, and the
+// "which material functions are missing" probe of
+// /root/reference/client/src/settings/shader-editor/Validate.tsx:8-57.
+#pragma once
+#include <set>
+#include <string>
+#include <vector>
+
+namespace rmb {
+
+struct UniformDecl {
+    std::string type;   // GLSL type name: float, int, uint, bool, vec2.., ivec2.., uvec2.., mat2..
+    std::string name;
+    int array_size = 0; // 0 = not an array
+    int line = 0;       // 1-based line in the scene source
+};
+
+struct LowerResult {
+    bool ok = false;
+    std::string error;                  // GL-style message when !ok
+    std::string body;                   // lowered scene text, same line structure as the input
+    std::vector<UniformDecl> uniforms;  // scene-declared uniforms, removed from `body`
+    std::set<std::string> functions;    // functions DEFINED at global scope
+    bool pure = true;                   // no mutable per-invocation state reachable from scene code
+};
+
+LowerResult lower_scene(const std::string& glsl);
+
+// The seven material functions every program must define and their default bodies
+// (Validate.tsx:18-51), already in lowered form.
+struct DefaultFunction {
+    const char* name;
+    const char* text;
+};
+const std::vector<DefaultFunction>& default_material_functions();
+
+// GLSL type -> (base type: 'f','i','u','b', component count, is matrix columns)
+bool uniform_type_info(const std::string& type, char* base, int* components);
+
+}  // namespace rmb

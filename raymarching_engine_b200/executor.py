@@ -1,0 +1,306 @@
+"""Render-job host layer: the Python mirror of the reference's TypeScript renderer, with the
+WebGL2 calls replaced by the C ABI of libraymarch_b200.so.
+
+Mirrors (paths under /root/reference/client/src):
+  renderer/LoadRenderJobContext.tsx:268-287   loadRenderJobContext      -> load_render_job_context
+  renderer/LoadRenderJobContext.tsx:162-250   fbo.create / fbo.delete   -> RenderJobContext.fbo
+  renderer/ShaderCache.tsx:91-119             programCache.getProgram   -> RenderJobContext.program_cache
+  renderer/RenderJobExecutor.tsx:77-341       doRenderJob               -> do_render_job
+  index.tsx:25-59                             makePresenter             -> make_presenter
+Names, argument meaning, loop order and error behaviour follow the reference; errors are values
+(`{"success": False, "why": {"type": ..., "infoLog": ...}}`), never exceptions.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass
+from typing import Callable, Dict, Generator, Optional
+
+import numpy as np
+
+from . import _lib
+from .halton import halton
+from .schema import RenderJobSchema
+from .uniforms import UniformData, set_uniform_array, set_uniform_matrix4, set_uniforms, u
+
+L = _lib.lib
+
+
+@dataclass
+class ShaderError:                       # ShaderCache.tsx:8-11 (+ "general", RenderJobExecutor.tsx:73-75)
+    type: str                            # "vertex" | "fragment" | "program" | "general"
+    infoLog: str
+
+
+class Program:
+    def __init__(self, context: "RenderJobContext", handle: int):
+        self.context, self.handle = context, handle
+
+    def source(self) -> str:
+        return L.rmb_program_source(self.handle).decode()
+
+    def kernel_attr(self, kernel: int):
+        r, l = C.c_int(-1), C.c_int(-1)
+        L.rmb_program_kernel_attr(self.handle, kernel, C.byref(r), C.byref(l))
+        return r.value, l.value
+
+
+class FramebufferInfo:                   # RenderJobFramebufferInfo, RenderJobExecutor.tsx:14-30
+    def __init__(self, context: "RenderJobContext", handle: int, width: int, height: int, frameid: int):
+        self.context, self.handle = context, handle
+        self.width, self.height, self.frameid = width, height, frameid
+        self.local_rows = L.rmb_fb_local_rows(handle)
+
+    def global_rows(self) -> np.ndarray:
+        return np.array([L.rmb_fb_global_row(self.handle, r) for r in range(self.local_rows)], dtype=np.int64)
+
+    _PLANES = {"color": (0, np.float32, 4), "normalAndDofRadius": (1, np.uint16, 4), "albedoAndDepth": (2, np.uint16, 4),
+               "depth": (3, np.float32, 1), "rgba8": (4, np.uint8, 4)}
+
+    def read(self, plane: str) -> np.ndarray:
+        which, dt, ch = self._PLANES[plane]
+        shape = (self.local_rows, self.width, ch) if ch > 1 else (self.local_rows, self.width)
+        out = np.empty(shape, dtype=dt)
+        st = L.rmb_fb_read(self.context.handle, self.handle, which, out.ctypes.data_as(C.c_void_p), out.nbytes)
+        if st != _lib.RMB_OK:
+            raise RuntimeError(self.context.last_error())
+        return out
+
+    def write(self, plane: str, arr: np.ndarray) -> None:
+        which, dt, ch = self._PLANES[plane]
+        a = np.ascontiguousarray(arr, dtype=dt)
+        st = L.rmb_fb_write(self.context.handle, self.handle, which, a.ctypes.data_as(C.c_void_p), a.nbytes)
+        if st != _lib.RMB_OK:
+            raise RuntimeError(self.context.last_error())
+
+    def device_ptr(self, plane: str) -> int:
+        return L.rmb_fb_device_ptr(self.handle, self._PLANES[plane][0])
+
+
+class _Fbo:
+    """context.fbo of the reference (LoadRenderJobContext.tsx:184-249); pool semantics live in C."""
+
+    def __init__(self, context: "RenderJobContext"):
+        self._c = context
+
+    def create(self, width: int, height: int, frameid: int) -> Optional[FramebufferInfo]:
+        h = L.rmb_fb_acquire(self._c.handle, int(width), int(height), int(frameid))
+        if not h:
+            return None
+        return FramebufferInfo(self._c, h, int(width), int(height), int(frameid))
+
+    def delete(self, width: int, height: int, frameid: int) -> None:
+        L.rmb_fb_release(self._c.handle, int(width), int(height), int(frameid))
+
+
+class _ProgramCache:
+    """context.programCache (ShaderCache.tsx:91-119).  `getProgram` returns a Program or a ShaderError."""
+
+    def __init__(self, context: "RenderJobContext"):
+        self._c = context
+
+    def get_program(self, scene_source: str, flavour: Optional[int] = None, spec: Optional[Dict[str, UniformData]] = None):
+        flavour = self._c.flavour if flavour is None else flavour
+        arr, n = _lib.make_spec_array(spec)
+        out = C.c_void_p()
+        etype = C.create_string_buffer(16)
+        log = C.create_string_buffer(1 << 16)
+        src = scene_source.encode()
+        st = L.rmb_program_get(self._c.handle, src, len(src), flavour, arr, n, C.byref(out), etype, log, len(log))
+        if st != _lib.RMB_OK:
+            return ShaderError(etype.value.decode() or "general", log.value.decode())
+        return Program(self._c, out.value)
+
+
+class RenderJobContext:                  # RenderJobExecutor.tsx:32-54
+    def __init__(self, handle: int, device: int, rank: int, n_ranks: int, tile_rows: int, flavour: int, specialize: bool):
+        self.handle = handle
+        self.device, self.rank, self.n_ranks, self.tile_rows = device, rank, n_ranks, tile_rows
+        self.flavour, self.specialize = flavour, specialize
+        self.fbo = _Fbo(self)
+        self.program_cache = _ProgramCache(self)
+
+    def last_error(self) -> str:
+        return (L.rmb_last_error(self.handle) or b"").decode()
+
+    def stream(self) -> int:
+        return L.rmb_ctx_stream(self.handle)
+
+    def sync(self) -> None:
+        L.rmb_sync(self.handle)
+
+    def counters(self, reset: bool = False):
+        out = (C.c_uint64 * 2)()
+        L.rmb_counters_read(self.handle, out, 1 if reset else 0)
+        return int(out[0]), int(out[1])
+
+    def present(self, fb: FramebufferInfo, brightness: float, want_depth: bool = True):
+        """display pass + readback: (rgba8[local_rows, W, 4] uint8, depth[local_rows, W] float32 | None)"""
+        rgba = np.empty((fb.local_rows, fb.width, 4), dtype=np.uint8)
+        depth = np.empty((fb.local_rows, fb.width), dtype=np.float32) if want_depth else None
+        st = L.rmb_present(self.handle, fb.handle, float(np.float32(brightness)), rgba.ctypes.data_as(C.c_void_p),
+                           depth.ctypes.data_as(C.c_void_p) if want_depth else None)
+        if st != _lib.RMB_OK:
+            raise RuntimeError(self.last_error())
+        return rgba, depth
+
+    def close(self) -> None:
+        if self.handle:
+            L.rmb_ctx_destroy(self.handle)
+            self.handle = None
+
+
+def load_render_job_context(device: int = 0, rank: int = 0, n_ranks: int = 1, tile_rows: int = 16,
+                            flavour: int = _lib.FLAVOUR_EXACT, specialize: bool = True) -> Optional[RenderJobContext]:
+    """loadRenderJobContext(gl) (LoadRenderJobContext.tsx:268-287): returns None when any piece
+    of the context cannot be created (the reference returns undefined)."""
+    h = L.rmb_ctx_create(device, rank, n_ranks, tile_rows)
+    if not h:
+        return None
+    return RenderJobContext(h, device, rank, n_ranks, tile_rows, flavour, specialize)
+
+
+def context_error() -> str:
+    return (L.rmb_last_error(None) or b"").decode()
+
+
+# RenderJobExecutor.tsx:70-71: module-level generators that are never reset
+_render_job_halton2 = halton(2)
+_render_job_halton3 = halton(3)
+
+
+def reset_halton() -> None:
+    """Test hook: restart the two module-level Halton generators (a page reload in the reference)."""
+    global _render_job_halton2, _render_job_halton3
+    _render_job_halton2, _render_job_halton3 = halton(2), halton(3)
+
+
+def _gen_err(info_log: str) -> ShaderError:      # RenderJobExecutor.tsx:73-75
+    return ShaderError("general", info_log)
+
+
+def builtin_uniforms(schema: RenderJobSchema, rand_noise) -> Dict[str, UniformData]:
+    """The uniform record of RenderJobExecutor.tsx:212-264."""
+    mode = schema.camera.mode
+    mode_index = ["perspective", "orthographic", "panoramic"].index(mode.type) if mode.type in ("perspective", "orthographic", "panoramic") else -1
+    counts = schema.reflectionIterationCounts
+    return {
+        "blendWithPreviousFactor": u.float(schema.render.blendWithPreviousFrameFactor),
+        "previousColor": u.int(0),
+        "previousNormalAndDofRadius": u.int(1),
+        "previousAlbedoAndDepth": u.int(2),
+        "randNoise": u.vec2(rand_noise[0], rand_noise[1]),
+        "position": u.vec3(*schema.camera.position),
+        "dofAmount": u.float(schema.dof.amount),
+        "dofFocalPlaneDistance": u.float(schema.dof.distance),
+        "cameraMode": u.int(mode_index),
+        "fov": u.float(mode.fov if mode.type == "perspective" else mode.size if mode.type == "orthographic" else 1),
+        "reflections": u.float(len(counts)),
+        "raymarchingSteps": u.float(counts[0] if counts else math.nan),
+        "indirectLightingRaymarchingSteps": u.float(counts[1] if len(counts) > 1 else (counts[0] if counts else math.nan)),
+        "aspect": u.float(schema.render.width / schema.render.height),
+        "fogDensity": u.float(schema.fogDensity),
+        "exposure": u.float(schema.render.exposure / schema.render.samplesPerPixel),
+        "blendMode": u.int(1 if schema.render.blendMode == "additive" else 0),
+        "renderMode": u.int(1 if schema.render.renderMode == "preview" else 0),
+        "lightCount": u.int(len(schema.lights)),
+        "showDofFocalPlane": u.int(1 if schema.dof.showFocusedArea else 0),
+    }
+
+
+def upload_sample_uniforms(program: Program, schema: RenderJobSchema, rand_noise) -> None:
+    """Everything RenderJobExecutor.tsx:212-297 uploads before the draw call, in the same order."""
+    set_uniforms(program, builtin_uniforms(schema, rand_noise))
+    set_uniforms(program, schema.customShaderParameters)                                   # :266
+    set_uniform_array(program, "raymarchingStepCountsArray", 1, list(schema.reflectionIterationCounts))   # :268-274
+    if len(schema.lights) > 0:                                                             # :276-291
+        pos, col, size = [], [], []
+        for l in schema.lights:
+            pos += list(l.position if l.type == "point" else l.direction)
+            col += list(l.color)
+            size.append(l.size if l.type == "point" else 0)
+        set_uniform_array(program, "lightPositions", 3, pos)
+        set_uniform_array(program, "lightColors", 3, col)
+        set_uniform_array(program, "lightSizes", 1, size)
+    set_uniform_matrix4(program, "rotation", list(schema.camera.rotation))                 # :293-297
+
+
+PresentFn = Callable[[RenderJobContext, RenderJobSchema, FramebufferInfo, int], None]
+
+
+def do_render_job(schema: RenderJobSchema, context: RenderJobContext):
+    """doRenderJob (RenderJobExecutor.tsx:77-341).  Returns a function that takes the `present`
+    callback and returns a generator; the generator yields None every `sampleYieldInterval`
+    samples and returns {"success": bool, "why": ShaderError | None}."""
+    framebuffers = context.fbo.create(schema.render.width, schema.render.height, schema.render.frameid)   # :106-110
+    if framebuffers is None:
+        def failed(_present):
+            return {"success": False, "why": _gen_err("Failed to load framebuffers.")}       # :112-119
+            yield  # pragma: no cover
+        return failed
+
+    spec = dict(schema.customShaderParameters) if context.specialize else None
+    program = context.program_cache.get_program(schema.sdfShaderSource, None, spec)          # :121-127
+    if not isinstance(program, Program):
+        def failed(_present):
+            return {"success": False, "why": program}                                        # :129-136
+            yield  # pragma: no cover
+        return failed
+
+    def run(present: PresentFn) -> Generator[None, None, dict]:
+        samples_rendered_so_far = 0
+        r = schema.render
+        for y_partitions in range(r.subdivisions):                                           # :148-162
+            for x_partitions in range(r.subdivisions):
+                for _sample_index in range(r.samplesPerPixel):
+                    if samples_rendered_so_far % r.sampleYieldInterval == 0:                 # :163-166
+                        present(context, schema, framebuffers, samples_rendered_so_far)
+                        yield
+                    x1 = math.floor((r.width / r.subdivisions) * x_partitions)               # :167-180
+                    y1 = math.floor((r.height / r.subdivisions) * y_partitions)
+                    x2 = math.ceil((r.width / r.subdivisions) * (x_partitions + 1))
+                    y2 = math.ceil((r.height / r.subdivisions) * (y_partitions + 1))
+                    rand_noise = (next(_render_job_halton2), next(_render_job_halton3))      # :219-222
+                    upload_sample_uniforms(program, schema, rand_noise)
+                    # gl.scissor(x1, y1, x2, y2): the reference passes the far corner where GL expects
+                    # width/height (RenderJobExecutor.tsx:182); reproduced as is.
+                    st = L.rmb_render_sample(context.handle, program.handle, framebuffers.handle, x1, y1, x2, y2)   # :299 + blit :301-326
+                    if st != _lib.RMB_OK:
+                        return {"success": False, "why": _gen_err(context.last_error())}
+                    samples_rendered_so_far += 1
+        context.fbo.delete(r.width, r.height, r.frameid)                                     # :333-337
+        present(context, schema, framebuffers, samples_rendered_so_far)                      # :338
+        return {"success": True, "why": None}
+
+    return run
+
+
+def make_presenter(samples_up_to_this_point: int, sink: Optional[dict] = None, want_depth: bool = True) -> PresentFn:
+    """makePresenter (index.tsx:25-59): display pass with brightness = 1 / samplesUpToThisPoint (the
+    host's own counter; the generator's samplesSoFar argument is ignored, as in the reference).
+    The canvas is replaced by `sink`: the latest frame lands in sink["rgba8"], sink["depth"]."""
+    def present(context: RenderJobContext, schema: RenderJobSchema, framebuffers: FramebufferInfo, _samples_so_far: int) -> None:
+        brightness = 1 / samples_up_to_this_point if samples_up_to_this_point else math.inf
+        rgba, depth = context.present(framebuffers, brightness, want_depth)
+        if sink is not None:
+            sink["rgba8"], sink["depth"] = rgba, depth
+            sink["presents"] = sink.get("presents", 0) + 1
+    return present
+
+
+def run_job(schema: RenderJobSchema, context: RenderJobContext, samples_up_to_this_point: Optional[int] = None) -> dict:
+    """Convenience: pump a job to completion like the rAF loop of index.tsx:236-263 and return
+    {"success", "why", "rgba8", "depth"}."""
+    sink: dict = {}
+    n = samples_up_to_this_point if samples_up_to_this_point is not None else schema.render.samplesPerPixel * schema.render.subdivisions ** 2
+    gen = do_render_job(schema, context)(make_presenter(n, sink))
+    result = None
+    try:
+        while True:
+            next(gen)
+    except StopIteration as stop:
+        result = stop.value
+    out = dict(result or {"success": False, "why": _gen_err("generator ended without a result")})
+    out.update(sink)
+    return out

@@ -1,0 +1,73 @@
+"""Uniform value records.  Mirrors /root/reference/client/src/renderer/Uniforms.tsx:1-46
+(`UniformData = {type: "f"|"i"|"ui", count: 1..4, data}`, namespace `u`, `setUniforms`)."""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Mapping, Sequence
+
+from . import _lib
+
+
+@dataclass(frozen=True)
+class UniformData:
+    type: str            # "f" | "i" | "ui"      Uniforms.tsx:8
+    count: int           # 1..4                  Uniforms.tsx:1-5
+    data: tuple
+
+    def __post_init__(self):
+        if self.type not in ("f", "i", "ui"):
+            raise ValueError(f"bad uniform type {self.type!r}")
+        if not (1 <= self.count <= 4) or len(self.data) != self.count:
+            raise ValueError("uniform count must be 1..4 and match len(data)")
+
+
+class u:  # noqa: N801  (name follows Uniforms.tsx:11 `export namespace u`)
+    @staticmethod
+    def float(x) -> UniformData:
+        return UniformData("f", 1, (x,))
+
+    @staticmethod
+    def vec2(x, y) -> UniformData:
+        return UniformData("f", 2, (x, y))
+
+    @staticmethod
+    def vec3(x, y, z) -> UniformData:
+        return UniformData("f", 3, (x, y, z))
+
+    @staticmethod
+    def vec4(x, y, z, w) -> UniformData:
+        return UniformData("f", 4, (x, y, z, w))
+
+    @staticmethod
+    def int(x) -> UniformData:
+        return UniformData("i", 1, (x,))
+
+
+_TYPE = {"f": (_lib.UNIFORM_F, C.c_float), "i": (_lib.UNIFORM_I, C.c_int32), "ui": (_lib.UNIFORM_UI, C.c_uint32)}
+
+
+def set_uniforms(program, uniforms: Mapping[str, UniformData]) -> None:
+    """`setUniforms(gl, program, uniforms)` (Uniforms.tsx:34-46): gl.uniform{count}{type}v per entry.
+    Unknown names are ignored like a null uniform location."""
+    for name, s in uniforms.items():
+        code, ct = _TYPE[s.type]
+        buf = (ct * s.count)(*[ct(v).value for v in s.data])
+        st = _lib.lib.rmb_uniform_set(program.handle, name.encode(), code, s.count, C.cast(buf, C.c_void_p))
+        if st != _lib.RMB_OK:
+            raise RuntimeError(f"uniform {name}: {program.context.last_error()}")
+
+
+def set_uniform_array(program, name: str, components: int, values: Sequence[float]) -> None:
+    """gl.uniform1fv / gl.uniform3fv on an array uniform (RenderJobExecutor.tsx:268-291)."""
+    n = len(values) // components
+    if n == 0:
+        return
+    buf = (C.c_float * (n * components))(*[float(v) for v in values[: n * components]])
+    _lib.lib.rmb_uniform_set_array(program.handle, name.encode(), _lib.UNIFORM_F, components, n, C.cast(buf, C.c_void_p))
+
+
+def set_uniform_matrix4(program, name: str, m16: Sequence[float]) -> None:
+    """gl.uniformMatrix4fv(loc, false, m) (RenderJobExecutor.tsx:293-297): column-major."""
+    buf = (C.c_float * 16)(*[float(v) for v in m16])
+    _lib.lib.rmb_uniform_matrix4(program.handle, name.encode(), buf)
