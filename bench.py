@@ -1,0 +1,381 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of the hot path (BASELINE.json: megapixels/s and Msteps/s on the
+default scene at 1080p, 1/2/4/8 B200, against the reference shader run on the CPU).
+
+A "step" is one frame of the synthetic camera path: one raymarch sample of the default scene
+(scenes/guide.glsl with its @default uniforms, reference-default preview mode) at 1920x1080 into a
+fresh framebuffer, followed by the display pass.  Pose 0 of the path is the reference's start-up
+view (camera at the origin looking down +z); pose k orbits bigSphereCenter
+at radius 10 by 2*pi*k/256 (config 5).
+
+  value      frames resident in HBM (no host copies in the timed region), CUDA events on the
+             library's stream, summed over K steps, max over ranks
+  e2e        the same frames through the public API (raymarching_engine_b200.run_job = do_render_job +
+             presenter): uniforms from host memory, RGBA8 + fp32 depth read back to pinned host
+             memory every step, host wall clock, max over ranks
+  roofline   the raymarch kernel against the FP32 FMA pipe (this path is FP32-bound, not HBM- or
+             tensor-bound: SURVEY.md 8d): executed SDF evaluations (counted by the kernel) x 282
+             algorithmic flop per preview step / kernel time
+  --impl reference   the CPU restatement of the reference shader (oracle/, see its header: the
+             reference itself needs a browser WebGL stack that does not exist here) on all host cores
+
+N > 1 (torchrun): every rank renders its own poses of the path (weak scaling, no data-path
+collective); `--shard tiles` instead splits each frame into interleaved 16-row tiles and gathers the
+RGBA8 rows to rank 0 with NCCL (BASELINE.json config 3).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+FLOP_PER_PREVIEW_STEP = 282.0   # 272 per SDF evaluation + 10 for advance/depth/compares
+FLOP_PER_CASTRAY_STEP = 278.0
+N_POSES = 256
+
+
+def orbit_pose(k: int):
+    """Pose k of the synthetic camera path: radius 10 around bigSphereCenter = (0,0,10) in the XZ
+    plane, looking at the centre.  rotation = gl-matrix mat4.fromYRotation(-theta), column-major."""
+    theta = 2.0 * math.pi * (k % N_POSES) / N_POSES
+    c, s = math.cos(theta), math.sin(theta)
+    position = (10.0 * s, 0.0, 10.0 - 10.0 * c)
+    phi = -theta
+    cp, sp = math.cos(phi), math.sin(phi)
+    rotation = (cp, 0.0, -sp, 0.0, 0.0, 1.0, 0.0, 0.0, sp, 0.0, cp, 0.0, 0.0, 0.0, 0.0, 1.0)
+    # forward = rotation * (0,0,1) = (sp, 0, cp) = (-sin theta, 0, cos theta): towards the centre
+    return position, rotation
+
+
+def make_schema(rm, src, custom, W, H, mode, pose, frameid):
+    s = rm.default_schema(src, custom, width=W, height=H, renderMode=mode, frameid=frameid)
+    s.camera.position, s.camera.rotation = orbit_pose(pose)
+    if mode == "full":
+        s.lights = [rm.default_light()]
+    return s
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks and throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.device, self.rows, self.proc = device, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); power.append(float(f[2]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_reference_sample(W, H, mode, band_rows, nthreads=None):
+    """Times the CPU restatement of the reference shader (oracle/) on a band of `band_rows` rows of
+    one W x H frame (every pixel costs the same in the reference: no early exit), plus the display
+    pass scaled to the band.  Returns (Mpx/s, seconds, cores, description)."""
+    sys.path.insert(0, str(ROOT / "oracle"))
+    import pyoracle
+    import raymarching_engine_b200.params as params
+    import raymarching_engine_b200.schema as schema_mod
+    src = (ROOT / "scenes" / "guide.glsl").read_text()
+    custom = params.default_custom_settings(src)
+    s = schema_mod.default_schema(src, custom, width=W, height=H, renderMode=mode)
+    if mode == "full":
+        s.lights = [schema_mod.default_light()]
+    cores = nthreads or os.cpu_count() or 1
+    acc = pyoracle.Accumulators(W, H)
+    U = pyoracle.uniforms_from_schema(s, (0.5, 1.0 / 3.0))
+    y0 = max(0, (H - band_rows) // 2)
+    t0 = time.perf_counter()
+    pyoracle.render_sample("guide", custom, U, acc, (0, y0, W, band_rows), cores)
+    t1 = time.perf_counter()
+    pyoracle.display(acc, 1.0, cores)
+    t2 = time.perf_counter()
+    px = W * min(band_rows, H)
+    secs = (t1 - t0) + (t2 - t1) * (px / (W * H))
+    return px / secs / 1e6, secs, cores, f"{W}x{min(band_rows, H)} band of one {W}x{H} {mode}-mode frame, raymarch + display, {cores} threads"
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path.  The reference cannot be
+    executed here (TypeScript + GLSL in a browser; no Node, browser or GL stack in this image), so this
+    arm times oracle/ - the CPU restatement of its shader - on all host cores (kind "port")."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    W, H = args.width, args.height
+    band = args.ref_band_rows
+    vals = []
+    for i in range(args.warmup + args.steps):
+        mpx, secs, cores, desc = cpu_reference_sample(W, H, args.mode, band)
+        if i >= args.warmup:
+            vals.append((mpx, secs))
+    total_s = sum(s for _, s in vals)
+    px = W * min(band, H) * len(vals)
+    value = px / total_s / 1e6
+    line = {
+        "impl": "reference", "metric": metric_name(args), "value": value, "unit": "Mpx/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total_s / max(len(vals), 1), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args),
+        "cpu_baseline": {"value": value, "unit": "Mpx/s", "cores": cores, "kind": "port", "sample": "each step: " + desc},
+        "e2e": {"value": value, "unit": "Mpx/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "extra": {"msteps_per_s_ref_equiv": value * ref_steps_per_px(args)},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def ref_steps_per_px(args) -> float:
+    return 128.0 if args.mode == "preview" else 384.0 * 2 + 25.0
+
+
+def metric_name(args) -> str:
+    return f"megapixels/s, default scene (guide.glsl) {args.width}x{args.height}, {args.mode} mode"
+
+
+def workload_config(args) -> dict:
+    return {"workload": f"guide.glsl default scene, {args.width}x{args.height}, {args.mode} mode, 1 spp/frame, "
+                        f"256-pose orbit camera path (pose 0 = reference start-up view), fresh framebuffer per frame",
+            "flavour": args.flavour, "shard": args.shard if args.gpus > 1 else "none",
+            "l2": "flushed between steps (256 MiB device memset, untimed)",
+            "steps_per_px_reference": ref_steps_per_px(args)}
+
+
+def run_b200(args):
+    import numpy as np
+    import torch
+    import raymarching_engine_b200 as rm
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    W, H = args.width, args.height
+    flavour = rm.FLAVOUR_FAST if args.flavour == "fast" else rm.FLAVOUR_EXACT
+    tiles = world > 1 and args.shard == "tiles"
+    ctx = rm.load_render_job_context(device=local, rank=rank if tiles else 0, n_ranks=world if tiles else 1, tile_rows=16, flavour=flavour)
+    if ctx is None:
+        raise SystemExit("bench.py: " + rm.context_error())
+    src = (ROOT / "scenes" / "guide.glsl").read_text()
+    custom = rm.default_custom_settings(src)
+    stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local))
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    L = rm._lib.lib
+
+    prog = ctx.program_cache.get_program(src, None, custom)
+    if not isinstance(prog, rm.Program):
+        raise SystemExit("bench.py: program failed to compile: " + prog.infoLog)
+    regs = prog.kernel_attr(0 if args.mode == "preview" else 1)
+
+    frame_counter = [1]
+
+    def pose_of(step):   # weak scaling: rank r renders poses r, r+world, ...; tiles: everyone renders pose `step`
+        return step if tiles else step * world + rank
+
+    def device_step(step, ev=None):
+        """one frame, everything resident in HBM; returns nothing (async)"""
+        frame_counter[0] += 1
+        s = make_schema(rm, src, custom, W, H, args.mode, pose_of(step), frame_counter[0])
+        fb = ctx.fbo.create(W, H, s.render.frameid)
+        rm.upload_sample_uniforms(prog, s, (0.5, 1.0 / 3.0))
+        if ev:
+            ev[0].record(stream)
+        st = L.rmb_render_sample(ctx.handle, prog.handle, fb.handle, 0, 0, W, H)
+        if ev:
+            ev[1].record(stream)
+        assert st == 0, ctx.last_error()
+        st = L.rmb_present_device(ctx.handle, fb.handle, 1.0)
+        assert st == 0, ctx.last_error()
+        if tiles:
+            gather_tiles(fb)
+        ctx.fbo.delete(W, H, s.render.frameid)
+
+    gather_state = {}
+
+    def gather_tiles(fb):
+        # NCCL gather of each rank's RGBA8 rows to rank 0: equal-sized padded
+        # buffers (ranks own 1..2 tiles more or less), issued in the library's stream order
+        if "send" not in gather_state:
+            max_rows = -(-H // (16 * world)) * 16
+            gather_state["send"] = torch.zeros(max_rows * W * 4, dtype=torch.uint8, device="cuda")
+            gather_state["recv"] = [torch.empty_like(gather_state["send"]) for _ in range(world)] if rank == 0 else None
+        n = fb.local_rows * W * 4
+        st = L.rmb_fb_copy_to_device(ctx.handle, fb.handle, 4, gather_state["send"].data_ptr(), n)
+        assert st == 0, ctx.last_error()
+        with torch.cuda.stream(stream):
+            dist.gather(gather_state["send"], gather_state["recv"], dst=0)
+
+    def e2e_step(step):
+        frame_counter[0] += 1
+        s = make_schema(rm, src, custom, W, H, args.mode, pose_of(step), frame_counter[0])
+        rm.reset_halton()   # every frame of the path uses randNoise = (1/2, 1/3), like device_step
+        out = rm.run_job(s, ctx)
+        assert out["success"], out["why"]
+        return out
+
+    def barrier():
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up (also compiles the program variant) ----
+    for i in range(max(args.warmup, 3)):
+        device_step(i)
+    ctx.sync()
+    ctx.counters(reset=True)
+
+    sampler = ClockSampler(local)
+    sampler.start()
+
+    # ---- timed: device-resident ----
+    step_ms, kern_ms = [], []
+    barrier()
+    for i in range(args.steps):
+        flush_buf.zero_()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        device_step(args.warmup + i, (k0, k1))
+        e1.record(stream)
+        e1.synchronize()
+        step_ms.append(e0.elapsed_time(e1))
+        kern_ms.append(k0.elapsed_time(k1))
+    barrier()
+    evals, pxs = ctx.counters(reset=True)
+    total_ms = sum(step_ms)
+    if dist:
+        t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    frames = args.steps * (1 if tiles else world)
+    value = frames * W * H / (total_ms * 1e-3) / 1e6
+
+    # ---- timed: end to end through the public API ----
+    for i in range(2):
+        e2e_step(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        e2e_step(args.warmup + i)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    barrier()
+    if dist:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = frames * W * H / e2e_s / 1e6
+    clocks = sampler.stop()
+
+    # ---- roofline of the raymarch kernel ----
+    fp32_measured = ctx.measure_fp32_peak(0.5)
+    sm_count = torch.cuda.get_device_properties(local).multi_processor_count
+    sm_max = clocks.get("sm_max_mhz") or 1965.0
+    nominal_peak = sm_count * 128 * 2 * sm_max * 1e6 / 1e12
+    flop_per_step = FLOP_PER_PREVIEW_STEP if args.mode == "preview" else FLOP_PER_CASTRAY_STEP
+    kernel_s = sum(kern_ms) * 1e-3
+    achieved = evals * flop_per_step / kernel_s / 1e12 if kernel_s > 0 else 0.0
+    roofline = {
+        "bound": "fp32", "achieved": achieved, "peak": nominal_peak, "unit": "TFLOP/s", "frac": achieved / nominal_peak, "traffic": None,
+        "peak_source": f"derived: {sm_count} SMs x 128 FP32 lanes x 2 x {sm_max:.0f} MHz (MEASURED_PEAKS.json has no FP32 figure; BASELINE.md section 2)",
+        "peak_measured_ffma": fp32_measured, "frac_of_measured_ffma": achieved / fp32_measured if fp32_measured else None,
+        "kernel": "rm_preview_kernel" if args.mode == "preview" else "rm_full_kernel",
+        "kernel_ms_avg": 1e3 * kernel_s / max(args.steps, 1), "kernel_share_of_step": kernel_s / (sum(step_ms) * 1e-3),
+        "executed_sdf_evals_per_launch": evals / max(args.steps, 1), "flop_per_step": flop_per_step,
+        "executed_steps_per_px": evals / max(pxs, 1), "registers_per_thread": regs[0], "local_bytes": regs[1],
+    }
+
+    line = {
+        "metric": metric_name(args), "value": value, "unit": "Mpx/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": total_ms / max(args.steps, 1), "higher_is_better": True, "scaling": "strong" if tiles else "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args),
+        "roofline": roofline,
+        "e2e": {"value": e2e_value, "unit": "Mpx/s", "h2d_bytes_per_step": 712, "d2h_bytes_per_step": W * H * 8,
+                "ms_per_step": 1e3 * e2e_s / max(args.steps, 1)},
+        "gpu_launches": 2 * args.steps,   # rm_*_kernel + rm_display_kernel per step (device-resident loop)
+        "clocks": clocks,
+        "extra": {"msteps_per_s_ref_equiv": value * ref_steps_per_px(args), "e2e_msteps_per_s_ref_equiv": e2e_value * ref_steps_per_px(args)},
+    }
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        mpx, secs, cores, desc = cpu_reference_sample(W, H, args.mode, args.cpu_band_rows)
+        line["cpu_baseline"] = {"value": mpx, "unit": "Mpx/s", "cores": cores, "kind": "port", "sample": desc, "seconds": secs}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if dist:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--width", type=int, default=1920)
+    ap.add_argument("--height", type=int, default=1080)
+    ap.add_argument("--mode", default="preview", choices=["preview", "full"])
+    ap.add_argument("--flavour", default="exact", choices=["exact", "fast"])
+    ap.add_argument("--shard", default="poses", choices=["poses", "tiles"])
+    ap.add_argument("--cpu-band-rows", type=int, default=360)
+    ap.add_argument("--ref-band-rows", type=int, default=120)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -144,6 +144,9 @@ void* rmb_fb_device_ptr(rmb_fb* fb, int which);
 size_t rmb_fb_plane_bytes(rmb_fb* fb, int which);
 rmb_status rmb_fb_read(rmb_ctx* ctx, rmb_fb* fb, int which, void* host, size_t bytes);
 rmb_status rmb_fb_write(rmb_ctx* ctx, rmb_fb* fb, int which, const void* host, size_t bytes);
+/* asynchronous device-to-device copy of a plane on the context's stream (multi-GPU tile gather:
+ * the caller hands the destination to NCCL in the same stream order) */
+rmb_status rmb_fb_copy_to_device(rmb_ctx* ctx, rmb_fb* fb, int which, void* dst_device, size_t bytes);
 /* out[0] = SDF evaluations executed, out[1] = pixel-samples rendered, since the last reset */
 rmb_status rmb_counters_read(rmb_ctx* ctx, uint64_t out[2], int reset);
 /* evaluates the scene's sdf() and material functions at n points: in n*3 floats, out n*17 floats
@@ -154,6 +157,9 @@ rmb_status rmb_probe(rmb_ctx* ctx, rmb_program* prog, const float* points_xyz, i
 rmb_status rmb_compile_only(const char* scene_glsl, size_t scene_len, int flavour, const rmb_spec_uniform* spec,
                             int n_spec, char* infolog, size_t infolog_cap, void* cubin_out, size_t cubin_cap,
                             size_t* cubin_bytes, char* source_out, size_t source_cap);
+/* FP32 FMA throughput of this GPU in TFLOP/s (register-only FFMA kernel, best of `seconds` of
+ * launches): the roofline denominator for this FP32-bound path. */
+rmb_status rmb_measure_fp32_peak(rmb_ctx* ctx, double seconds, double* tflops);
 /* pinned host memory for the caller's readback buffers */
 void* rmb_host_alloc(size_t bytes);
 void rmb_host_free(void* p);

@@ -25,9 +25,11 @@
 //   src/settings/shader-editor/Validate.tsx:18-51 default material functions
 //   public/examples/*.glsl, dist/examples/sphere-grid.glsl, src/index.tsx:365-389  scenes
 //
-// Arithmetic: scalar fp32, no FMA contraction (-ffp-contract=off), GLSL built-ins from the
-// shared deterministic math layer (glsl_rt.h / rm_math.h, exact policy) so that the CUDA kernel
-// can be compared bit for bit.  Scenes are hand-translated here, independently of
+// Arithmetic: scalar fp32, no compiler FMA contraction (-ffp-contract=off); the only fused
+// operations are the ones pinned explicitly (glsl_rt.h header: dot/length, mod, mix, and the march
+// advance p + d*s / depth += deltaZ*s below - contractions GLSL ES 3.00 4.5.2 permits and GPU
+// compilers perform).  GLSL built-ins come from the shared deterministic math layer (glsl_rt.h /
+// rm_math.h, exact policy) so that the CUDA kernel can be compared bit for bit.  Scenes are hand-translated here, independently of
 // the product's GLSL->CUDA lowering, so the lowering itself is under test.
 #include <cstdint>
 #include <cstdio>
@@ -196,12 +198,14 @@ struct SceneMenger : DefaultMaterials {                             // examples/
     }
 };
 
-// GLSL `v.ab *= mat2(c, -s, s, c)`: row vector times column-major matrix.
+// GLSL `v.ab *= mat2(c, -s, s, c)`: row vector times column-major matrix:
+// columns c0 = (c, -s), c1 = (s, c);  (a,b)*M = (dot((a,b),c0), dot((a,b),c1)), with the pinned
+// (fused) dot of glsl_rt.h.
 static inline void rotPair(float& a, float& b, float ang) {
     float c = cos(ang), s = sin(ang);
-    // columns: c0 = (c, -s), c1 = (s, c);  (a,b)*M = (dot((a,b),c0), dot((a,b),c1))
-    float na = a * c + b * (-s);
-    float nb = a * s + b * c;
+    vec2 v(a, b);
+    float na = dot(v, vec2(c, -s));
+    float nb = dot(v, vec2(s, c));
     a = na; b = nb;
 }
 
@@ -403,7 +407,7 @@ struct Frag {
     vec3 castRay(vec3 rayPosition, vec3 rayDirection, float steps) {  // raymarcher.frag:163-170
         for (float i = 0.0f; i < steps; i++) {
             float sdfNow = sdf(rayPosition);
-            rayPosition = rayPosition + rayDirection * sdfNow;
+            rayPosition = fmaV(rayDirection, sdfNow, rayPosition);   // p + d*s contracted to one fma per component (pinned)
         }
         return rayPosition;
     }
@@ -452,8 +456,8 @@ struct Frag {
             for (float i = 0.0f; i < n; i++) {
                 float sdfNow = sdf(rayPosition);
                 if (sdfNow < 100000000000.0f) {
-                    rayPosition = rayPosition + rayDirection * sdfNow;
-                    depth += deltaZ * sdfNow;
+                    rayPosition = fmaV(rayDirection, sdfNow, rayPosition);   // contracted (pinned)
+                    depth = g_fma(deltaZ, sdfNow, depth);
                 }
                 if (sdfNow > 0.0001f) stepsTaken = i;
             }
@@ -661,7 +665,7 @@ static void exit_steps_t(const float* custom, int ncustom, const OrcUniforms* U,
         for (int i = 0; i < n; i++) {
             float s = S.sdf(p);
             if (!(s < 100000000000.0f)) { e = i + 1; break; }
-            vec3 q = p + d * s;
+            vec3 q = fmaV(d, s, p);
             if (rmx::f2i(q.x) == rmx::f2i(p.x) && rmx::f2i(q.y) == rmx::f2i(p.y) && rmx::f2i(q.z) == rmx::f2i(p.z)) { e = i + 1; break; }
             p = q;
         }

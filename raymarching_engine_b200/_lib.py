@@ -23,8 +23,8 @@ EXPORTED_SYMBOLS = [
     "rmb_program_get", "rmb_program_source", "rmb_program_kernel_attr", "rmb_uniform_set", "rmb_uniform_set_array",
     "rmb_uniform_matrix4", "rmb_fb_acquire", "rmb_fb_release", "rmb_fb_local_rows", "rmb_fb_global_row",
     "rmb_render_sample", "rmb_present", "rmb_present_device", "rmb_fb_device_ptr", "rmb_fb_plane_bytes",
-    "rmb_fb_read", "rmb_fb_write", "rmb_counters_read", "rmb_probe", "rmb_compile_only", "rmb_host_alloc",
-    "rmb_host_free",
+    "rmb_fb_read", "rmb_fb_write", "rmb_fb_copy_to_device", "rmb_counters_read", "rmb_probe", "rmb_compile_only", "rmb_host_alloc",
+    "rmb_host_free", "rmb_measure_fp32_peak",
 ]
 
 
@@ -68,9 +68,11 @@ def _load() -> C.CDLL:
         "rmb_fb_plane_bytes": (sz, [vp, i]),
         "rmb_fb_read": (i, [vp, vp, i, vp, sz]),
         "rmb_fb_write": (i, [vp, vp, i, vp, sz]),
+        "rmb_fb_copy_to_device": (i, [vp, vp, i, vp, sz]),
         "rmb_counters_read": (i, [vp, C.POINTER(C.c_uint64), i]),
         "rmb_probe": (i, [vp, vp, vp, i, vp]),
         "rmb_compile_only": (i, [cp, sz, i, C.POINTER(SpecUniform), i, cp, sz, vp, sz, C.POINTER(sz), cp, sz]),
+        "rmb_measure_fp32_peak": (i, [vp, C.c_double, C.POINTER(C.c_double)]),
         "rmb_host_alloc": (vp, [sz]),
         "rmb_host_free": (None, [vp]),
     }

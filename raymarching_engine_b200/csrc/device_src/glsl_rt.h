@@ -16,11 +16,16 @@
 // __constant__ uniforms.
 //
 // Pinned choices for behaviour GLSL ES 3.00 leaves implementation-defined:
-//   length(v) = sqrt(x*x + y*y + z*z) unscaled, summed left to right;
-//   normalize(v) = v / length(v) (three divisions);  dot() summed left to right;
+//   dot(a,b) = fma(a.z,b.z, fma(a.y,b.y, a.x*b.x)) - the contraction GLSL permits (ES 3.00 4.5.2)
+//     and GPU compilers perform; length(v) = sqrt(dot(v,v)) unscaled;
+//   vector / scalar = vector * (1/scalar) with a correctly rounded reciprocal (within the 2.5 ULP
+//     GLSL allows for division; GPU drivers lower division to reciprocal-multiply as well);
+//     scalar / scalar and vector / vector are IEEE divisions;
+//   mod(x,y) = fma(-y, floor(x * (1/y)), x);  mix(a,b,t) = fma(b, t, a*(1-t));
+//   normalize(v) = v / length(v) (one reciprocal, three multiplies);
 //   min/max drop NaN operands (IEEE minNum/maxNum, -0 < +0) like CUDA fminf/fmaxf;
-//   round() rounds half away from zero;  mod(x,y) = x - y*floor(x/y) unfused;
-//   mix(a,b,t) = a*(1-t) + b*t;  mat*vec sums column contributions left to right.
+//   round() rounds half away from zero;  mat*vec sums column contributions left to right;
+//   every other a*b+c stays unfused (two roundings).
 //
 // Reference: the built-ins used by client/public/shader/raymarcher.frag and
 // client/public/examples/*.glsl of radian628/raymarching-engine.
@@ -44,9 +49,13 @@ RM_HD float g_add(float a, float b) { return a + b; }
 RM_HD float g_sub(float a, float b) { return a - b; }
 RM_HD float g_mul(float a, float b) { return a * b; }
 RM_HD float g_div(float a, float b) { return __fdividef(a, b); }
-RM_HD float g_sqrt(float a) { return sqrtf(a); }
-RM_HD float g_rsqrt(float a) { return rsqrtf(a); }
+RM_HD float g_sqrt(float a) { float r; asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(a)); return r; }
+RM_HD float g_rsqrt(float a) { float r; asm("rsqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(a)); return r; }
 RM_HD float g_floor(float a) { return floorf(a); }
+RM_HD float g_fma(float a, float b, float c) { return fmaf(a, b, c); }
+// plain division (the fast flavour compiles with --prec-div=false): folds when the divisor is a
+// compile-time constant, otherwise an approximate reciprocal
+RM_HD float g_rcp(float a) { return 1.0f / a; }
 #elif RM_DEVICE_CODE
 RM_HD float g_add(float a, float b) { return __fadd_rn(a, b); }
 RM_HD float g_sub(float a, float b) { return __fsub_rn(a, b); }
@@ -55,6 +64,14 @@ RM_HD float g_div(float a, float b) { return __fdiv_rn(a, b); }
 RM_HD float g_sqrt(float a) { return __fsqrt_rn(a); }
 RM_HD float g_rsqrt(float a) { return __fdiv_rn(1.0f, __fsqrt_rn(a)); }
 RM_HD float g_floor(float a) { return floorf(a); }
+RM_HD float g_fma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+#if defined(RM_FLAVOUR_FAST) && RM_FLAVOUR_FAST
+// inside a fast-flavour program (--prec-div=false) the exact namespace must not depend on flags
+RM_HD float g_rcp(float a) { return __fdiv_rn(1.0f, a); }
+#else
+// written as a plain IEEE division (--prec-div=true) so that a constant divisor folds at compile time
+RM_HD float g_rcp(float a) { return 1.0f / a; }
+#endif
 #else
 RM_HD float g_add(float a, float b) { return a + b; }
 RM_HD float g_sub(float a, float b) { return a - b; }
@@ -63,6 +80,8 @@ RM_HD float g_div(float a, float b) { return a / b; }
 RM_HD float g_sqrt(float a) { return __builtin_sqrtf(a); }
 RM_HD float g_rsqrt(float a) { return 1.0f / __builtin_sqrtf(a); }
 RM_HD float g_floor(float a) { return __builtin_floorf(a); }
+RM_HD float g_fma(float a, float b, float c) { return __builtin_fmaf(a, b, c); }
+RM_HD float g_rcp(float a) { return 1.0f / a; }
 #endif
 
 #if RM_DEVICE_CODE
@@ -139,11 +158,11 @@ RM_HD float round(float x) {
     return t;
 }
 RM_HD float fract(float x) { return g_sub(x, g_floor(x)); }
-RM_HD float mod(float x, float y) { return g_sub(x, g_mul(y, g_floor(g_div(x, y)))); }
+RM_HD float mod(float x, float y) { return g_fma(-y, g_floor(g_mul(x, g_rcp(y))), x); }
 RM_HD float min(float a, float b) { return g_min(a, b); }
 RM_HD float max(float a, float b) { return g_max(a, b); }
 RM_HD float clamp(float x, float lo, float hi) { return g_min(g_max(x, lo), hi); }
-RM_HD float mix(float a, float b, float t) { return g_add(g_mul(a, g_sub(1.0f, t)), g_mul(b, t)); }
+RM_HD float mix(float a, float b, float t) { return g_fma(b, t, g_mul(a, g_sub(1.0f, t))); }
 RM_HD float mix(float a, float b, bool t) { return t ? b : a; }
 RM_HD float step(float edge, float x) { return x < edge ? 0.0f : 1.0f; }
 RM_HD float smoothstep(float e0, float e1, float x) {
@@ -341,15 +360,16 @@ RM_HD bvec3 not_(bvec3 v) { return bvec3(!v.x, !v.y, !v.z); }
 RM_HD bvec4 not_(bvec4 v) { return bvec4(!v.x, !v.y, !v.z, !v.w); }
 
 // ------------------------------------------------------------------ component-wise operators
-#define GLSL_BINOP(op, fn)                                                                          \
+#define GLSL_BINOP(op, fn) GLSL_BINOP2(op, fn, fn)
+#define GLSL_BINOP2(op, fn, fns)                                                                    \
     RM_HD vec2 operator op(const vec2& a, const vec2& b) { return vec2(fn(a.x, b.x), fn(a.y, b.y)); } \
-    RM_HD vec2 operator op(const vec2& a, float b) { return vec2(fn(a.x, b), fn(a.y, b)); }          \
+    RM_HD vec2 operator op(const vec2& a, float b) { return vec2(fns(a.x, b), fns(a.y, b)); }        \
     RM_HD vec2 operator op(float a, const vec2& b) { return vec2(fn(a, b.x), fn(a, b.y)); }          \
     RM_HD vec3 operator op(const vec3& a, const vec3& b) { return vec3(fn(a.x, b.x), fn(a.y, b.y), fn(a.z, b.z)); } \
-    RM_HD vec3 operator op(const vec3& a, float b) { return vec3(fn(a.x, b), fn(a.y, b), fn(a.z, b)); } \
+    RM_HD vec3 operator op(const vec3& a, float b) { return vec3(fns(a.x, b), fns(a.y, b), fns(a.z, b)); } \
     RM_HD vec3 operator op(float a, const vec3& b) { return vec3(fn(a, b.x), fn(a, b.y), fn(a, b.z)); } \
     RM_HD vec4 operator op(const vec4& a, const vec4& b) { return vec4(fn(a.x, b.x), fn(a.y, b.y), fn(a.z, b.z), fn(a.w, b.w)); } \
-    RM_HD vec4 operator op(const vec4& a, float b) { return vec4(fn(a.x, b), fn(a.y, b), fn(a.z, b), fn(a.w, b)); } \
+    RM_HD vec4 operator op(const vec4& a, float b) { return vec4(fns(a.x, b), fns(a.y, b), fns(a.z, b), fns(a.w, b)); } \
     RM_HD vec4 operator op(float a, const vec4& b) { return vec4(fn(a, b.x), fn(a, b.y), fn(a, b.z), fn(a, b.w)); } \
     RM_HD vec2& operator op##=(vec2& a, const vec2& b) { a = a op b; return a; }                     \
     RM_HD vec2& operator op##=(vec2& a, float b) { a = a op b; return a; }                           \
@@ -360,8 +380,16 @@ RM_HD bvec4 not_(bvec4 v) { return bvec4(!v.x, !v.y, !v.z, !v.w); }
 GLSL_BINOP(+, g_add)
 GLSL_BINOP(-, g_sub)
 GLSL_BINOP(*, g_mul)
-GLSL_BINOP(/, g_div)
+// vector / scalar multiplies by the (correctly rounded) reciprocal of the scalar
+RM_HD float g_div_by_scalar(float a, float b) { return g_mul(a, g_rcp(b)); }
+GLSL_BINOP2(/, g_div, g_div_by_scalar)
 #undef GLSL_BINOP
+#undef GLSL_BINOP2
+// fused multiply-add of vectors: a*b + c with one rounding per component (used by the pipeline
+// for `rayPosition + rayDirection * sdfNow`, which GLSL compilers contract)
+RM_HD vec2 fmaV(const vec2& a, float b, const vec2& c) { return vec2(g_fma(a.x, b, c.x), g_fma(a.y, b, c.y)); }
+RM_HD vec3 fmaV(const vec3& a, float b, const vec3& c) { return vec3(g_fma(a.x, b, c.x), g_fma(a.y, b, c.y), g_fma(a.z, b, c.z)); }
+RM_HD vec4 fmaV(const vec4& a, float b, const vec4& c) { return vec4(g_fma(a.x, b, c.x), g_fma(a.y, b, c.y), g_fma(a.z, b, c.z), g_fma(a.w, b, c.w)); }
 
 RM_HD vec2 operator-(const vec2& a) { return vec2(-a.x, -a.y); }
 RM_HD vec3 operator-(const vec3& a) { return vec3(-a.x, -a.y, -a.z); }
@@ -445,9 +473,9 @@ GLSL_CMP(equal, ==) GLSL_CMP(notEqual, !=)
 #undef GLSL_CMP
 
 // ------------------------------------------------------------------ geometric functions
-RM_HD float dot(const vec2& a, const vec2& b) { return g_add(g_mul(a.x, b.x), g_mul(a.y, b.y)); }
-RM_HD float dot(const vec3& a, const vec3& b) { return g_add(g_add(g_mul(a.x, b.x), g_mul(a.y, b.y)), g_mul(a.z, b.z)); }
-RM_HD float dot(const vec4& a, const vec4& b) { return g_add(g_add(g_add(g_mul(a.x, b.x), g_mul(a.y, b.y)), g_mul(a.z, b.z)), g_mul(a.w, b.w)); }
+RM_HD float dot(const vec2& a, const vec2& b) { return g_fma(a.y, b.y, g_mul(a.x, b.x)); }
+RM_HD float dot(const vec3& a, const vec3& b) { return g_fma(a.z, b.z, g_fma(a.y, b.y, g_mul(a.x, b.x))); }
+RM_HD float dot(const vec4& a, const vec4& b) { return g_fma(a.w, b.w, g_fma(a.z, b.z, g_fma(a.y, b.y, g_mul(a.x, b.x)))); }
 RM_HD float length(const vec2& a) { return g_sqrt(dot(a, a)); }
 RM_HD float length(const vec3& a) { return g_sqrt(dot(a, a)); }
 RM_HD float length(const vec4& a) { return g_sqrt(dot(a, a)); }
@@ -455,9 +483,9 @@ RM_HD float distance(const vec2& a, const vec2& b) { return length(a - b); }
 RM_HD float distance(const vec3& a, const vec3& b) { return length(a - b); }
 RM_HD float distance(const vec4& a, const vec4& b) { return length(a - b); }
 #if GLSL_FAST
-RM_HD vec2 normalize(const vec2& a) { return a * rsqrtf(dot(a, a)); }
-RM_HD vec3 normalize(const vec3& a) { return a * rsqrtf(dot(a, a)); }
-RM_HD vec4 normalize(const vec4& a) { return a * rsqrtf(dot(a, a)); }
+RM_HD vec2 normalize(const vec2& a) { return a * g_rsqrt(dot(a, a)); }
+RM_HD vec3 normalize(const vec3& a) { return a * g_rsqrt(dot(a, a)); }
+RM_HD vec4 normalize(const vec4& a) { return a * g_rsqrt(dot(a, a)); }
 #else
 RM_HD vec2 normalize(const vec2& a) { return a / length(a); }
 RM_HD vec3 normalize(const vec3& a) { return a / length(a); }

@@ -32,27 +32,33 @@
 namespace rmx {
 
 // ---------------------------------------------------------------- bit casts / primitives
+// Bit casts go through memcpy on both sides (not the __double_as_longlong family): NVVM folds a
+// memcpy bit cast at compile time, which lets calls with constant arguments - pow(uniform, i) in
+// a specialised scene program - evaluate at compile time; the nvvm cast intrinsics do not fold.
 #if RM_DEVICE_CODE
-RM_HD long long d2ll(double x) { return __double_as_longlong(x); }
-RM_HD double ll2d(long long x) { return __longlong_as_double(x); }
-RM_HD int f2i(float x) { return __float_as_int(x); }
-RM_HD float i2f(int x) { return __int_as_float(x); }
+#define RM_MEMCPY memcpy
 RM_HD double dfma(double a, double b, double c) { return fma(a, b, c); }
-RM_HD double drint(double x) { return rint(x); }
 RM_HD double dfloor(double x) { return floor(x); }
 RM_HD double dsqrt(double x) { return sqrt(x); }
-RM_HD double dabs(double x) { return fabs(x); }
 #else
-RM_HD long long d2ll(double x) { long long r; memcpy(&r, &x, 8); return r; }
-RM_HD double ll2d(long long x) { double r; memcpy(&r, &x, 8); return r; }
-RM_HD int f2i(float x) { int r; memcpy(&r, &x, 4); return r; }
-RM_HD float i2f(int x) { float r; memcpy(&r, &x, 4); return r; }
+#define RM_MEMCPY __builtin_memcpy
 RM_HD double dfma(double a, double b, double c) { return __builtin_fma(a, b, c); }
-RM_HD double drint(double x) { return __builtin_rint(x); }   // round-to-nearest-even mode assumed
 RM_HD double dfloor(double x) { return __builtin_floor(x); }
 RM_HD double dsqrt(double x) { return __builtin_sqrt(x); }
-RM_HD double dabs(double x) { return __builtin_fabs(x); }
 #endif
+RM_HD long long d2ll(double x) { long long r; RM_MEMCPY(&r, &x, 8); return r; }
+RM_HD double ll2d(long long x) { double r; RM_MEMCPY(&r, &x, 8); return r; }
+RM_HD int f2i(float x) { int r; RM_MEMCPY(&r, &x, 4); return r; }
+RM_HD float i2f(int x) { float r; RM_MEMCPY(&r, &x, 4); return r; }
+RM_HD double dabs(double x) { return ll2d(d2ll(x) & 0x7fffffffffffffffLL); }
+// round to nearest even integer by the 2^52+2^51 trick: two IEEE additions, exact for
+// |x| < 2^51, identity above (such doubles are already integers)
+RM_HD double drint(double x) {
+    const double M = 6755399441055744.0;
+    if (!(dabs(x) < 2251799813685248.0)) return x;
+    double t = x + M;
+    return t - M;
+}
 
 RM_HD bool f_isnan(float x) { return (f2i(x) & 0x7fffffff) > 0x7f800000; }
 RM_HD bool f_isinf(float x) { return (f2i(x) & 0x7fffffff) == 0x7f800000; }

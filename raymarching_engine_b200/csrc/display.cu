@@ -85,6 +85,28 @@ __global__ void __launch_bounds__(256) rm_display_kernel(const float4* __restric
 }  // namespace disp
 }  // namespace xg
 
+// FP32 FMA throughput probe: the roofline denominator for this FP32-bound path is not in
+// MEASURED_PEAKS.json (which has HBM and bf16 only), so bench.py measures it live.  Each thread
+// runs 8 independent FFMA chains; 2 flop per FFMA.
+__global__ void __launch_bounds__(256) rm_fp32_peak_kernel(float* out, int iters, float a, float b) {
+    float x0 = threadIdx.x, x1 = x0 + 1.0f, x2 = x0 + 2.0f, x3 = x0 + 3.0f, x4 = x0 + 4.0f, x5 = x0 + 5.0f, x6 = x0 + 6.0f, x7 = x0 + 7.0f;
+#pragma unroll 1
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            x0 = fmaf(x0, a, b); x1 = fmaf(x1, a, b); x2 = fmaf(x2, a, b); x3 = fmaf(x3, a, b);
+            x4 = fmaf(x4, a, b); x5 = fmaf(x5, a, b); x6 = fmaf(x6, a, b); x7 = fmaf(x7, a, b);
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+}
+
+// Launches the probe with `blocks` blocks of 256 threads; flops = blocks*256*iters*16*8*2.
+extern "C" cudaError_t rmb_launch_fp32_peak(float* scratch, int blocks, int iters, cudaStream_t stream) {
+    rm_fp32_peak_kernel<<<blocks, 256, 0, stream>>>(scratch, iters, 0.999999f, 1e-7f);
+    return cudaGetLastError();
+}
+
 extern "C" cudaError_t rmb_launch_display(const void* color, const void* nd, void* rgba8, int W, int local_rows, int H,
                                           int tile_rows, int n_ranks, int rank, float brightness, cudaStream_t stream) {
     dim3 block(256, 1, 1), grid((unsigned)((W + 255) / 256), (unsigned)local_rows, 1);

@@ -206,7 +206,7 @@ const std::vector<DefaultFunction>& default_material_functions() {
     return v;
 }
 
-LowerResult lower_scene(const std::string& glsl) {
+LowerResult lower_scene(const std::string& glsl, const std::set<std::string>& constant_names) {
     LowerResult R;
     std::string trailing;
     std::vector<Token> T = tokenize(glsl, &trailing);
@@ -247,6 +247,33 @@ LowerResult lower_scene(const std::string& glsl) {
             auto rn = renames().find(t.text);
             if (rn != renames().end()) t.text = rn->second;
             if (rng_state_words().count(t.text)) R.pure = false;
+        }
+        if (t.kind == kIdent && t.text == "for" && brace > 0 && i + 1 < n && T[i + 1].text == "(") {
+            // constant-trip-count loop?  identifiers allowed in the header: type names, the loop
+            // variable(s) declared in the init clause, and baked uniforms
+            size_t k = i + 1;
+            int d = 0;
+            size_t close = 0;
+            while (k < n) {
+                if (T[k].text == "(") d++;
+                if (T[k].text == ")") { d--; if (d == 0) { close = k; break; } }
+                k++;
+            }
+            if (close) {
+                std::set<std::string> locals;
+                bool ok = true, init = true;
+                char bt; int bc;
+                for (size_t q = i + 2; q < close && ok; q++) {
+                    if (T[q].text == ";") init = false;
+                    if (T[q].kind != kIdent) continue;
+                    const std::string& w = T[q].text;
+                    if (uniform_type_info(w, &bt, &bc) || precision_words().count(w) || w == "const") continue;
+                    if (init && q > i + 2 && T[q - 1].kind == kIdent && uniform_type_info(T[q - 1].text, &bt, &bc)) { locals.insert(w); continue; }
+                    if (locals.count(w) || constant_names.count(w)) continue;
+                    ok = false;
+                }
+                if (ok && !locals.empty()) t.text = "_Pragma(\"unroll 32\") for";
+            }
         }
         if (brace == 0 && paren == 0 && t.kind == kIdent && at_decl_start) {
             // ---- global-scope declaration ----

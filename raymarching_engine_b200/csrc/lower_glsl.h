@@ -26,7 +26,11 @@ struct LowerResult {
     bool pure = true;                   // no mutable per-invocation state reachable from scene code
 };
 
-LowerResult lower_scene(const std::string& glsl);
+// `constant_names`: uniforms that will be compile-time constants in this program variant (baked).
+// A `for` loop whose header mentions only its own loop variable, literals and such constants gets
+// `_Pragma("unroll 32")`, so that specialised programs fully unroll short fractal loops and fold the
+// uniform-only sub-expressions (pow(), reciprocals) at compile time.
+LowerResult lower_scene(const std::string& glsl, const std::set<std::string>& constant_names = {});
 
 // The seven material functions every program must define and their default bodies
 // (Validate.tsx:18-51), already in lowered form.

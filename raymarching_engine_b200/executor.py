@@ -120,6 +120,7 @@ class RenderJobContext:                  # RenderJobExecutor.tsx:32-54
         self.flavour, self.specialize = flavour, specialize
         self.fbo = _Fbo(self)
         self.program_cache = _ProgramCache(self)
+        self._pinned_cache: dict = {}
 
     def last_error(self) -> str:
         return (L.rmb_last_error(self.handle) or b"").decode()
@@ -135,20 +136,51 @@ class RenderJobContext:                  # RenderJobExecutor.tsx:32-54
         L.rmb_counters_read(self.handle, out, 1 if reset else 0)
         return int(out[0]), int(out[1])
 
-    def present(self, fb: FramebufferInfo, brightness: float, want_depth: bool = True):
-        """display pass + readback: (rgba8[local_rows, W, 4] uint8, depth[local_rows, W] float32 | None)"""
-        rgba = np.empty((fb.local_rows, fb.width, 4), dtype=np.uint8)
-        depth = np.empty((fb.local_rows, fb.width), dtype=np.float32) if want_depth else None
+    def _pinned(self, key, shape, dtype) -> np.ndarray:
+        """numpy view of a cached pinned host buffer (rmb_host_alloc) for readbacks"""
+        k = (key, tuple(shape), np.dtype(dtype).str)
+        buf = self._pinned_cache.get(k)
+        if buf is None:
+            nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+            ptr = L.rmb_host_alloc(max(nbytes, 1))
+            if not ptr:
+                raise MemoryError("rmb_host_alloc failed")
+            arr = np.ctypeslib.as_array((C.c_uint8 * max(nbytes, 1)).from_address(ptr))[:nbytes].view(dtype).reshape(shape)
+            buf = (ptr, arr)
+            self._pinned_cache[k] = buf
+        return buf[1]
+
+    def present(self, fb: FramebufferInfo, brightness: float, want_depth: bool = True, readback: bool = True):
+        """display pass (+ readback into pinned host memory): (rgba8[local_rows, W, 4] uint8,
+        depth[local_rows, W] float32 | None).  The arrays are views of buffers reused by the next
+        present of the same size - copy them to keep them.  readback=False runs the display pass
+        only (the canvas of the reference is never read back either) and returns (None, None)."""
+        if not readback:
+            st = L.rmb_present_device(self.handle, fb.handle, float(np.float32(brightness)))
+            if st != _lib.RMB_OK:
+                raise RuntimeError(self.last_error())
+            return None, None
+        rgba = self._pinned("rgba", (fb.local_rows, fb.width, 4), np.uint8)
+        depth = self._pinned("depth", (fb.local_rows, fb.width), np.float32) if want_depth else None
         st = L.rmb_present(self.handle, fb.handle, float(np.float32(brightness)), rgba.ctypes.data_as(C.c_void_p),
                            depth.ctypes.data_as(C.c_void_p) if want_depth else None)
         if st != _lib.RMB_OK:
             raise RuntimeError(self.last_error())
         return rgba, depth
 
+    def measure_fp32_peak(self, seconds: float = 0.5) -> float:
+        out = C.c_double(0.0)
+        if L.rmb_measure_fp32_peak(self.handle, seconds, C.byref(out)) != _lib.RMB_OK:
+            raise RuntimeError(self.last_error())
+        return out.value
+
     def close(self) -> None:
         if self.handle:
             L.rmb_ctx_destroy(self.handle)
             self.handle = None
+            for ptr, _arr in self._pinned_cache.values():
+                L.rmb_host_free(ptr)
+            self._pinned_cache.clear()
 
 
 def load_render_job_context(device: int = 0, rank: int = 0, n_ranks: int = 1, tile_rows: int = 16,
@@ -276,15 +308,21 @@ def do_render_job(schema: RenderJobSchema, context: RenderJobContext):
     return run
 
 
-def make_presenter(samples_up_to_this_point: int, sink: Optional[dict] = None, want_depth: bool = True) -> PresentFn:
+def make_presenter(samples_up_to_this_point: int, sink: Optional[dict] = None, want_depth: bool = True,
+                   readback: str = "always") -> PresentFn:
     """makePresenter (index.tsx:25-59): display pass with brightness = 1 / samplesUpToThisPoint (the
-    host's own counter; the generator's samplesSoFar argument is ignored, as in the reference).
-    The canvas is replaced by `sink`: the latest frame lands in sink["rgba8"], sink["depth"]."""
-    def present(context: RenderJobContext, schema: RenderJobSchema, framebuffers: FramebufferInfo, _samples_so_far: int) -> None:
+    host's own counter; the generator's samplesSoFar argument is ignored for the brightness, as in
+    the reference).  The canvas is replaced by `sink`: the latest frame lands in sink["rgba8"],
+    sink["depth"] (views of pinned buffers).  readback="final" copies to the host only on the last
+    present of a job (the intermediate presents still run the display pass, like canvas redraws)."""
+    def present(context: RenderJobContext, schema: RenderJobSchema, framebuffers: FramebufferInfo, samples_so_far: int) -> None:
         brightness = 1 / samples_up_to_this_point if samples_up_to_this_point else math.inf
-        rgba, depth = context.present(framebuffers, brightness, want_depth)
+        total = schema.render.samplesPerPixel * schema.render.subdivisions ** 2
+        rb = readback == "always" or samples_so_far >= total
+        rgba, depth = context.present(framebuffers, brightness, want_depth, readback=rb)
         if sink is not None:
-            sink["rgba8"], sink["depth"] = rgba, depth
+            if rb:
+                sink["rgba8"], sink["depth"] = rgba, depth
             sink["presents"] = sink.get("presents", 0) + 1
     return present
 
@@ -294,7 +332,7 @@ def run_job(schema: RenderJobSchema, context: RenderJobContext, samples_up_to_th
     {"success", "why", "rgba8", "depth"}."""
     sink: dict = {}
     n = samples_up_to_this_point if samples_up_to_this_point is not None else schema.render.samplesPerPixel * schema.render.subdivisions ** 2
-    gen = do_render_job(schema, context)(make_presenter(n, sink))
+    gen = do_render_job(schema, context)(make_presenter(n, sink, readback="final"))
     result = None
     try:
         while True:

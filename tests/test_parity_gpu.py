@@ -1,0 +1,244 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same inputs.
+
+Tolerance (BASELINE.json north_star): RGBA8 within 1/255 on >= 99.9 % of pixels, hit depth within
+1e-4 relative.  The exact flavour is held to a stricter bar: bit-identical accumulators and bytes.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import pyoracle
+import raymarching_engine_b200 as rm
+from conftest import SCENES, scene_source
+
+pytestmark = pytest.mark.gpu
+
+
+def _schema(name, W, H, mode, lights=0, **kw):
+    src = scene_source(name)
+    s = rm.default_schema(src, rm.default_custom_settings(src), width=W, height=H, renderMode=mode, **kw)
+    if lights:
+        s.lights = [rm.default_light() for _ in range(lights)]
+    return s
+
+
+_FRAME = [1000]
+
+
+def _render_both(ctx, name, schema):
+    _FRAME[0] += 1
+    schema.render.frameid = _FRAME[0]
+    rm.reset_halton()
+    # keep the framebuffer alive for accumulator read-back: acquire before the job releases it
+    fb = ctx.fbo.create(schema.render.width, schema.render.height, schema.render.frameid)
+    got = rm.run_job(schema, ctx)
+    assert got["success"], got["why"]
+    planes = {p: fb.read(p) for p in ("color", "normalAndDofRadius", "albedoAndDepth", "depth")}
+    acc, want = pyoracle.run_job(name, schema)
+    return got, planes, acc, want
+
+
+def _assert_bit_exact(got, planes, acc, want):
+    np.testing.assert_array_equal(planes["color"].view(np.uint32), acc.color.view(np.uint32))
+    np.testing.assert_array_equal(planes["normalAndDofRadius"], acc.nd)
+    np.testing.assert_array_equal(planes["albedoAndDepth"], acc.ad)
+    np.testing.assert_array_equal(planes["depth"].view(np.uint32), acc.depth.view(np.uint32))
+    np.testing.assert_array_equal(got["rgba8"], want)
+
+
+@pytest.mark.parametrize("name", SCENES)
+def test_preview_bit_exact_all_scenes(ctx, name):
+    got, planes, acc, want = _render_both(ctx, name, _schema(name, 160, 90, "preview"))
+    _assert_bit_exact(got, planes, acc, want)
+
+
+@pytest.mark.parametrize("name", ["guide", "sphere-grid", "menger-sponge", "tree"])
+def test_full_bit_exact(ctx, name):
+    got, planes, acc, want = _render_both(ctx, name, _schema(name, 96, 54, "full", lights=1))
+    _assert_bit_exact(got, planes, acc, want)
+
+
+def test_full_two_lights_fog_mix(ctx):
+    s = _schema("guide", 64, 36, "full", lights=2, blendMode="mix", samplesPerPixel=2)
+    s.lights[1].position = (2.0, 3.0, 4.0)
+    s.lights[1].size = 0.5
+    s.fogDensity = 0.05
+    got, planes, acc, want = _render_both(ctx, "guide", s)
+    _assert_bit_exact(got, planes, acc, want)
+
+
+def test_multisample_subdivisions(ctx):
+    # 2x2 subdivisions x 3 spp: exercises the scissor quirk (x2,y2 passed as width,height) and Halton
+    s = _schema("guide", 100, 60, "preview", samplesPerPixel=3, subdivisions=2)
+    got, planes, acc, want = _render_both(ctx, "guide", s)
+    _assert_bit_exact(got, planes, acc, want)
+
+
+@pytest.mark.parametrize("mode", ["orthographic", "panoramic"])
+def test_camera_modes(ctx, mode):
+    s = _schema("guide", 128, 64, "preview")
+    s.camera.mode = rm.Orthographic(12.0) if mode == "orthographic" else rm.Panoramic()
+    got, planes, acc, want = _render_both(ctx, "guide", s)
+    _assert_bit_exact(got, planes, acc, want)
+
+
+def test_focal_plane_overlay_and_rotation(ctx):
+    s = _schema("guide", 128, 72, "preview")
+    s.dof.showFocusedArea = True
+    s.dof.distance = 6.0
+    c, sn = float(np.cos(0.3)), float(np.sin(0.3))
+    s.camera.rotation = (c, 0, -sn, 0, 0, 1, 0, 0, sn, 0, c, 0, 0, 0, 0, 1)
+    s.camera.position = (0.5, -0.25, 1.0)
+    got, planes, acc, want = _render_both(ctx, "guide", s)
+    _assert_bit_exact(got, planes, acc, want)
+
+
+def test_generic_program_matches_specialised(ctx):
+    # un-baked uniforms (constant memory) must give the same bits as the baked variant
+    s = _schema("guide", 96, 54, "preview")
+    spec_ctx = ctx
+    got_a, planes_a, acc, want = _render_both(spec_ctx, "guide", s)
+    gen = rm.load_render_job_context(device=0, specialize=False)
+    try:
+        got_b, planes_b, _, _ = _render_both(gen, "guide", s)
+    finally:
+        gen.close()
+    np.testing.assert_array_equal(planes_a["color"].view(np.uint32), planes_b["color"].view(np.uint32))
+    np.testing.assert_array_equal(got_a["rgba8"], got_b["rgba8"])
+    np.testing.assert_array_equal(got_a["rgba8"], want)
+
+
+def test_fast_flavour_is_close_but_not_the_parity_path(ctx):
+    """The fast flavour (FMA contraction + approximate intrinsics in scene code) is NOT the parity
+    path: stepsTaken of the preview branch flips by one step on ~0.1 % of pixels, so it sits at the
+    edge of the north_star tolerance (RGBA8 within 1/255 on >= 99.9 % of pixels).  bench.py headlines
+    the exact flavour; this test only guards against gross divergence and records the figure."""
+    s = _schema("guide", 320, 180, "preview")
+    fast = rm.load_render_job_context(device=0, flavour=rm.FLAVOUR_FAST)
+    try:
+        got, planes, acc, want = _render_both(fast, "guide", s)
+    finally:
+        fast.close()
+    diff = np.abs(got["rgba8"].astype(np.int32) - want.astype(np.int32)).max(axis=2)
+    frac_ok = float((diff <= 1).mean())
+    rel = np.abs(got["depth"] - acc.depth) / np.maximum(np.abs(acc.depth), 1e-30)
+    hit = acc.depth < 1e3
+    frac_depth = float((rel[hit] <= 1e-4).mean()) if hit.any() else 1.0
+    print(f"fast flavour: rgba8 within 1/255 on {frac_ok * 100:.3f} % of pixels; hit depth within 1e-4 on {frac_depth * 100:.3f} %")
+    assert frac_ok >= 0.99
+
+
+BUILTIN_SCENE = """
+uniform int op;
+uniform float b;
+float sdf(vec3 p) {
+  float a = p.x;
+  if (op == 0) return sin(a); if (op == 1) return cos(a); if (op == 2) return tan(a); if (op == 3) return pow(a, b);
+  if (op == 4) return exp(a); if (op == 5) return log(a); if (op == 6) return exp2(a); if (op == 7) return log2(a);
+  if (op == 8) return sqrt(a); if (op == 9) return inversesqrt(a); if (op == 10) return mod(a, b); if (op == 11) return fract(a);
+  if (op == 12) return floor(a); if (op == 13) return round(a); if (op == 14) return min(a, b); if (op == 15) return max(a, b);
+  if (op == 16) return atan(a, b); if (op == 17) return asin(a); if (op == 18) return acos(a); if (op == 19) return atan(a);
+  if (op == 20) return a / b; if (op == 21) return sinh(a); if (op == 22) return cosh(a); if (op == 23) return tanh(a);
+  if (op == 24) return sign(a); if (op == 25) return ceil(a); if (op == 26) return trunc(a); if (op == 27) return roundEven(a);
+  if (op == 28) return smoothstep(0.0, b, a); if (op == 29) return mix(a, b, 0.3);
+  if (op == 30) return asinh(a); if (op == 31) return acosh(a); if (op == 32) return atanh(a);
+  return 0.0;
+}
+"""
+
+
+def test_builtins_device_equals_host(ctx):
+    """Every GLSL built-in of the exact policy gives the same bits on sm_100 and on the host."""
+    prog = ctx.program_cache.get_program(BUILTIN_SCENE, rm.FLAVOUR_EXACT, None)
+    assert isinstance(prog, rm.Program), prog
+    rng = np.random.default_rng(7)
+    special = np.array([0.0, -0.0, 1.0, -1.0, 0.5, -0.5, 2.5, -2.5, 1e-30, -1e-30, 1e-45, 3.4e38, -3.4e38, np.inf, -np.inf, np.nan,
+                        700.5, 869.1, 1e6, 123456.789, 0.33333334, 3.0, 1.5, -1.5, 0.49999997, 8388609.0], np.float32)
+    a = np.concatenate([special, rng.normal(0, 1, 300).astype(np.float32), rng.uniform(-900, 900, 300).astype(np.float32),
+                        np.exp(rng.uniform(-40, 40, 200)).astype(np.float32)])
+    L = pyoracle.lib()
+    bad = []
+    for op in range(33):
+        for b in (2.0, 0.7, -3.0, 0.0):
+            rm.set_uniforms(prog, {"op": rm.u.int(op), "b": rm.u.float(b)})
+            pts = np.zeros((a.size, 3), np.float32)
+            pts[:, 0] = a
+            out = np.zeros((a.size, 17), np.float32)
+            st = rm._lib.lib.rmb_probe(ctx.handle, prog.handle, pts.ctypes.data_as(C.c_void_p), a.size, out.ctypes.data_as(C.c_void_p))
+            assert st == 0, ctx.last_error()
+            dev = out[:, 15]
+            host = np.array([L.orc_builtin(op, float(x), b) for x in a], np.float32)
+            both_nan = np.isnan(dev) & np.isnan(host)
+            neq = (dev.view(np.uint32) != host.view(np.uint32)) & ~both_nan
+            if neq.any():
+                i = int(np.flatnonzero(neq)[0])
+                bad.append((op, b, float(a[i]), float(dev[i]), float(host[i]), int(neq.sum())))
+    assert not bad, bad[:10]
+
+
+def test_probe_materials_match_oracle(ctx):
+    rng = np.random.default_rng(3)
+    pts = np.concatenate([rng.uniform(-12, 12, (200, 3)), rng.uniform(-60, 60, (100, 3))]).astype(np.float32)
+    L = pyoracle.lib()
+    for name in SCENES:
+        src = scene_source(name)
+        custom = rm.default_custom_settings(src)
+        prog = ctx.program_cache.get_program(src, rm.FLAVOUR_EXACT, custom)
+        assert isinstance(prog, rm.Program), prog
+        out = np.zeros((len(pts), 17), np.float32)
+        assert rm._lib.lib.rmb_probe(ctx.handle, prog.handle, pts.ctypes.data_as(C.c_void_p), len(pts), out.ctypes.data_as(C.c_void_p)) == 0
+        cu = pyoracle.flatten_custom(name, custom)
+        want = np.zeros((len(pts), 17), np.float32)
+        for i, p in enumerate(pts):
+            L.orc_materials(name.encode(), cu.ctypes.data_as(C.c_void_p) if cu.size else None, int(cu.size), float(p[0]), float(p[1]), float(p[2]),
+                            want[i].ctypes.data_as(C.c_void_p))
+        eq = (out.view(np.uint32) == want.view(np.uint32)) | (np.isnan(out) & np.isnan(want))
+        assert eq.all(), (name, np.argwhere(~eq)[:5], out[~eq][:5], want[~eq][:5])
+
+
+def test_compile_error_is_a_value(ctx):
+    bad = "float sdf(vec3 p) {\n  return lenght(p) - 1.0;\n}\n"
+    s = rm.default_schema(bad, {}, width=16, height=16)
+    res = rm.run_job(s, ctx)
+    assert res["success"] is False
+    assert res["why"].type == "fragment"
+    assert "0:147" in res["why"].infoLog      # scene line 2 -> 145 + 2 (GLSLEditor.tsx:134-136)
+
+
+def test_fb_pool_semantics(ctx):
+    # LoadRenderJobContext.tsx:186-249: reuse by size from purgatory, clear iff frameid differs
+    a = ctx.fbo.create(40, 30, 77001)
+    a.write("color", np.ones((30, 40, 4), np.float32))
+    assert ctx.fbo.create(40, 30, 77001).handle == a.handle
+    ctx.fbo.delete(40, 30, 77001)
+    b = ctx.fbo.create(40, 30, 77001)          # same frameid: contents kept
+    assert b.handle == a.handle and float(b.read("color").sum()) == 30 * 40 * 4
+    ctx.fbo.delete(40, 30, 77001)
+    c = ctx.fbo.create(40, 30, 77002)          # new frameid: cleared
+    assert c.handle == a.handle and float(c.read("color").sum()) == 0.0
+    ctx.fbo.delete(40, 30, 77002)
+
+
+def test_row_tile_sharding_reassembles(ctx):
+    # config 3 partitioning: 2 and 3 ranks with 16-row tiles on one device reproduce the 1-rank frame
+    s = _schema("guide", 128, 72, "preview")
+    got, planes, acc, want = _render_both(ctx, "guide", s)
+    for G in (2, 3):
+        full = np.zeros_like(want)
+        depth = np.zeros_like(acc.depth)
+        for r in range(G):
+            c = rm.load_render_job_context(device=0, rank=r, n_ranks=G, tile_rows=16)
+            try:
+                rm.reset_halton()
+                s.render.frameid = 5000 + 10 * G + r
+                fb = c.fbo.create(s.render.width, s.render.height, s.render.frameid)
+                res = rm.run_job(s, c)
+                assert res["success"]
+                rows = fb.global_rows()
+                full[rows] = res["rgba8"]
+                depth[rows] = res["depth"]
+            finally:
+                c.close()
+        np.testing.assert_array_equal(full, want)
+        np.testing.assert_array_equal(depth.view(np.uint32), acc.depth.view(np.uint32))
