@@ -361,6 +361,9 @@ struct Frag {
     vec4 fragColor, normalAndDofRadius, albedoAndDepth;
     bool wroteAux = false;
     float hitDepth = 0.0f;                                          // fp32 depth before fp16 storage (H5)
+    // trace of the last main() call, for the numpy cross-check (tests/test_oracle_numpy.py)
+    vec3 trOrigin, trDir, trEnd;
+    float trDeltaZ = 0.0f, trStepsTaken = 0.0f, trJitterX = 0.0f, trJitterY = 0.0f;
 
     Frag(const OrcUniforms& u, Scene& s, int w, int h) : U(u), S(s), W(w), H(h) {}
 
@@ -449,6 +452,8 @@ struct Frag {
             rayPosition = position;
         }
 
+        trOrigin = rayPosition; trDir = rayDirection; trDeltaZ = deltaZ;
+        trJitterX = randomDirectionOffset.x; trJitterY = randomDirectionOffset.y;
         if (U.renderMode == 1) {                                    // preview branch :207-244
             float stepsTaken = 0.0f;
             float depth = 0.0f;
@@ -473,6 +478,7 @@ struct Frag {
                 else fragColor = col;
             } else fragColor = col;
             hitDepth = depth;
+            trEnd = rayPosition; trStepsTaken = stepsTaken;
             return;                                                 // attachments 1,2 unwritten (H6)
         }
 
@@ -673,6 +679,21 @@ static void exit_steps_t(const float* custom, int ncustom, const OrcUniforms* U,
     }
 }
 
+// Trace of one preview-mode pixel for the independent numpy cross-check: out[17] = origin xyz,
+// direction xyz, deltaZ, jitter xy, end position xyz, stepsTaken, depth, rgb of the new sample.
+template <class Scene>
+static void trace_pixel_t(const float* custom, int ncustom, const OrcUniforms* U, int W, int H, int px, int py, float* out) {
+    Scene S;
+    if (ncustom == Scene::NU && ncustom) S.load(custom);
+    Frag<Scene> f(*U, S, W, H);
+    f.texcoord = vec2(((float)px + 0.5f) / (float)W, ((float)py + 0.5f) / (float)H);
+    Accum prev;
+    prev.color = vec4(0.0f); prev.normalAndDofRadius = vec4(0.0f); prev.albedoAndDepth = vec4(0.0f);
+    f.main(prev);
+    float o[17] = {f.trOrigin.x, f.trOrigin.y, f.trOrigin.z, f.trDir.x, f.trDir.y, f.trDir.z, f.trDeltaZ, f.trJitterX, f.trJitterY,
+                   f.trEnd.x, f.trEnd.y, f.trEnd.z, f.trStepsTaken, f.hitDepth, f.fragColor.x, f.fragColor.y, f.fragColor.z};
+    memcpy(out, o, sizeof(o));
+}
 #define ORC_SCENES(X)                      \
     X("guide", SceneGuide)                 \
     X("fractal1", SceneFractal1)           \
@@ -772,6 +793,13 @@ void orc_halton(int b, int n, double* out) {
 
 int orc_preview_exit_steps(const char* scene, const float* custom, int ncustom, const OrcUniforms* U, int W, int H, int* out) {
 #define X(name, T) if (!strcmp(scene, name)) { exit_steps_t<T>(custom, ncustom, U, W, H, out); return 0; }
+    ORC_SCENES(X)
+#undef X
+    return -1;
+}
+
+int orc_trace_pixel(const char* scene, const float* custom, int ncustom, const OrcUniforms* U, int W, int H, int px, int py, float* out17) {
+#define X(name, T) if (!strcmp(scene, name)) { trace_pixel_t<T>(custom, ncustom, U, W, H, px, py, out17); return 0; }
     ORC_SCENES(X)
 #undef X
     return -1;

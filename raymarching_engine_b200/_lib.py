@@ -24,7 +24,7 @@ EXPORTED_SYMBOLS = [
     "rmb_uniform_matrix4", "rmb_fb_acquire", "rmb_fb_release", "rmb_fb_local_rows", "rmb_fb_global_row",
     "rmb_render_sample", "rmb_present", "rmb_present_device", "rmb_fb_device_ptr", "rmb_fb_plane_bytes",
     "rmb_fb_read", "rmb_fb_write", "rmb_fb_copy_to_device", "rmb_counters_read", "rmb_probe", "rmb_compile_only", "rmb_host_alloc",
-    "rmb_host_free", "rmb_measure_fp32_peak",
+    "rmb_host_free", "rmb_measure_fp32_peak", "rmb_owned_rows_below",
 ]
 
 
@@ -73,6 +73,7 @@ def _load() -> C.CDLL:
         "rmb_probe": (i, [vp, vp, vp, i, vp]),
         "rmb_compile_only": (i, [cp, sz, i, C.POINTER(SpecUniform), i, cp, sz, vp, sz, C.POINTER(sz), cp, sz]),
         "rmb_measure_fp32_peak": (i, [vp, C.c_double, C.POINTER(C.c_double)]),
+        "rmb_owned_rows_below": (i, [i, i, i, i, i]),
         "rmb_host_alloc": (vp, [sz]),
         "rmb_host_free": (None, [vp]),
     }
