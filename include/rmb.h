@@ -136,6 +136,13 @@ rmb_status rmb_render_sample(rmb_ctx* ctx, rmb_program* prog, rmb_fb* fb, int sx
 rmb_status rmb_present(rmb_ctx* ctx, rmb_fb* fb, float brightness, uint8_t* rgba8_host, float* depth_host);
 /* display pass only; the RGBA8 result stays in device memory (rmb_fb_device_ptr(fb, 4)) */
 rmb_status rmb_present_device(rmb_ctx* ctx, rmb_fb* fb, float brightness);
+/* Non-blocking present, the shape of the reference's own present (WebGL draws are asynchronous,
+ * index.tsx:25-59; only toDataURL, index.tsx:470-476, waits): display pass on the context's stream,
+ * then the readbacks on a second stream so that they overlap the next frame's kernels.  The host
+ * buffers (pinned: rmb_host_alloc) are valid after rmb_present_wait(ctx, fb).  A later draw into the
+ * same framebuffer set waits for the readback on the device, never on the host. */
+rmb_status rmb_present_async(rmb_ctx* ctx, rmb_fb* fb, float brightness, uint8_t* rgba8_host, float* depth_host);
+rmb_status rmb_present_wait(rmb_ctx* ctx, rmb_fb* fb);
 
 /* ---- inspection (tests, benchmarks) --------------------------------------------------------- */
 /* which: 0 colour (float4), 1 normal+dofRadius (4 x binary16), 2 albedo+depth (4 x binary16),

@@ -22,7 +22,7 @@ EXPORTED_SYMBOLS = [
     "rmb_abi_version", "rmb_ctx_create", "rmb_ctx_destroy", "rmb_last_error", "rmb_ctx_stream", "rmb_sync",
     "rmb_program_get", "rmb_program_source", "rmb_program_kernel_attr", "rmb_uniform_set", "rmb_uniform_set_array",
     "rmb_uniform_matrix4", "rmb_fb_acquire", "rmb_fb_release", "rmb_fb_local_rows", "rmb_fb_global_row",
-    "rmb_render_sample", "rmb_present", "rmb_present_device", "rmb_fb_device_ptr", "rmb_fb_plane_bytes",
+    "rmb_render_sample", "rmb_present", "rmb_present_device", "rmb_present_async", "rmb_present_wait", "rmb_fb_device_ptr", "rmb_fb_plane_bytes",
     "rmb_fb_read", "rmb_fb_write", "rmb_fb_copy_to_device", "rmb_counters_read", "rmb_probe", "rmb_compile_only", "rmb_host_alloc",
     "rmb_host_free", "rmb_measure_fp32_peak", "rmb_owned_rows_below",
 ]
@@ -64,6 +64,8 @@ def _load() -> C.CDLL:
         "rmb_render_sample": (i, [vp, vp, vp, i, i, i, i]),
         "rmb_present": (i, [vp, vp, f, vp, vp]),
         "rmb_present_device": (i, [vp, vp, f]),
+        "rmb_present_async": (i, [vp, vp, f, vp, vp]),
+        "rmb_present_wait": (i, [vp, vp]),
         "rmb_fb_device_ptr": (vp, [vp, i]),
         "rmb_fb_plane_bytes": (sz, [vp, i]),
         "rmb_fb_read": (i, [vp, vp, i, vp, sz]),

@@ -49,9 +49,18 @@ RM_HD float g_add(float a, float b) { return a + b; }
 RM_HD float g_sub(float a, float b) { return a - b; }
 RM_HD float g_mul(float a, float b) { return a * b; }
 RM_HD float g_div(float a, float b) { return __fdividef(a, b); }
-RM_HD float g_sqrt(float a) { float r; asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(a)); return r; }
-RM_HD float g_rsqrt(float a) { float r; asm("rsqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(a)); return r; }
-RM_HD float g_floor(float a) { return floorf(a); }
+// single MUFU.SQRT / MUFU.RSQ (flush-to-zero forms: no denormal scaling code around them)
+RM_HD float g_sqrt(float a) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a)); return r; }
+RM_HD float g_rsqrt(float a) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a)); return r; }
+// floor on the FP32 pipe: FRND issues on the 16-lane XU pipe and was the top stall of the exact
+// flavour (profiles/r1_preview_exact_ncu_full.txt).  (a + 1.5*2^23) - 1.5*2^23 rounds to the nearest
+// integer for |a| <= 2^22; one compare-and-subtract turns that into floor.  Larger |a| take FRND.
+RM_HD float g_floor(float a) {
+    const float M = 12582912.0f;
+    const float t = __fadd_rn(__fadd_rn(a, M), -M);
+    const float r = t > a ? __fadd_rn(t, -1.0f) : t;
+    return fabsf(a) <= 4194304.0f ? r : floorf(a);
+}
 RM_HD float g_fma(float a, float b, float c) { return fmaf(a, b, c); }
 // plain division (the fast flavour compiles with --prec-div=false): folds when the divisor is a
 // compile-time constant, otherwise an approximate reciprocal
@@ -159,6 +168,30 @@ RM_HD float round(float x) {
 }
 RM_HD float fract(float x) { return g_sub(x, g_floor(x)); }
 RM_HD float mod(float x, float y) { return g_fma(-y, g_floor(g_mul(x, g_rcp(y))), x); }
+// Domain repetition idiom `mod(x + h1, s) - h2` (and `mod(x, s) - h2`): the lowering
+// (lower_glsl.cpp) hands the four operands to rm_rep / rm_rep0.  Exact policy: the expression as
+// written.  Fast policy: when h2 == s/2 (a centred cell, the canonical opRep form) it is the centred
+// remainder y - s*rint(y/s) of y = x + (h1 - h2): FFMA (y*(1/s) + 1.5*2^23), FADD, FFMA per component,
+// no floor at all; operands that are compile-time constants in a baked program fold the test away.
+#if GLSL_FAST
+RM_HD float rm_rep1(float x, float h1, float s, float h2) {
+    if (h2 == 0.5f * s && s > 0.0f && s < 1e30f) {
+        const float M = 12582912.0f;
+        const float y = (h1 == h2) ? x : x + (h1 - h2);
+        const float r = __fadd_rn(__fmaf_rn(y, 1.0f / s, M), -M);
+        return __fmaf_rn(-s, r, y);
+    }
+    return mod(x + h1, s) - h2;
+}
+#else
+RM_HD float rm_rep1(float x, float h1, float s, float h2) { return g_sub(mod(g_add(x, h1), s), h2); }
+#endif
+RM_HD float rm_rep(float x, float h1, float s, float h2) { return rm_rep1(x, h1, s, h2); }
+#if GLSL_FAST
+RM_HD float rm_rep0(float x, float s, float h2) { return rm_rep1(x, 0.0f, s, h2); }
+#else
+RM_HD float rm_rep0(float x, float s, float h2) { return g_sub(mod(x, s), h2); }
+#endif
 RM_HD float min(float a, float b) { return g_min(a, b); }
 RM_HD float max(float a, float b) { return g_max(a, b); }
 RM_HD float clamp(float x, float lo, float hi) { return g_min(g_max(x, lo), hi); }
@@ -432,6 +465,33 @@ GLSL_MAP2S(mod) GLSL_MAP2S(min) GLSL_MAP2S(max)
 #undef GLSL_MAP1
 #undef GLSL_MAP2
 #undef GLSL_MAP2S
+
+// component access for "float or vector" operands of the repetition idiom
+RM_HD float rm_c(float a, int) { return a; }
+RM_HD float rm_c(const vec2& a, int i) { return a[i]; }
+RM_HD float rm_c(const vec3& a, int i) { return a[i]; }
+RM_HD float rm_c(const vec4& a, int i) { return a[i]; }
+template <class H1, class S, class H2> RM_HD vec2 rm_rep(const vec2& x, const H1& h1, const S& s, const H2& h2) {
+    return vec2(rm_rep1(x.x, rm_c(h1, 0), rm_c(s, 0), rm_c(h2, 0)), rm_rep1(x.y, rm_c(h1, 1), rm_c(s, 1), rm_c(h2, 1)));
+}
+template <class H1, class S, class H2> RM_HD vec3 rm_rep(const vec3& x, const H1& h1, const S& s, const H2& h2) {
+    return vec3(rm_rep1(x.x, rm_c(h1, 0), rm_c(s, 0), rm_c(h2, 0)), rm_rep1(x.y, rm_c(h1, 1), rm_c(s, 1), rm_c(h2, 1)),
+                rm_rep1(x.z, rm_c(h1, 2), rm_c(s, 2), rm_c(h2, 2)));
+}
+template <class H1, class S, class H2> RM_HD vec4 rm_rep(const vec4& x, const H1& h1, const S& s, const H2& h2) {
+    return vec4(rm_rep1(x.x, rm_c(h1, 0), rm_c(s, 0), rm_c(h2, 0)), rm_rep1(x.y, rm_c(h1, 1), rm_c(s, 1), rm_c(h2, 1)),
+                rm_rep1(x.z, rm_c(h1, 2), rm_c(s, 2), rm_c(h2, 2)), rm_rep1(x.w, rm_c(h1, 3), rm_c(s, 3), rm_c(h2, 3)));
+}
+template <class S, class H2> RM_HD vec2 rm_rep0(const vec2& x, const S& s, const H2& h2) {
+    return vec2(rm_rep0(x.x, rm_c(s, 0), rm_c(h2, 0)), rm_rep0(x.y, rm_c(s, 1), rm_c(h2, 1)));
+}
+template <class S, class H2> RM_HD vec3 rm_rep0(const vec3& x, const S& s, const H2& h2) {
+    return vec3(rm_rep0(x.x, rm_c(s, 0), rm_c(h2, 0)), rm_rep0(x.y, rm_c(s, 1), rm_c(h2, 1)), rm_rep0(x.z, rm_c(s, 2), rm_c(h2, 2)));
+}
+template <class S, class H2> RM_HD vec4 rm_rep0(const vec4& x, const S& s, const H2& h2) {
+    return vec4(rm_rep0(x.x, rm_c(s, 0), rm_c(h2, 0)), rm_rep0(x.y, rm_c(s, 1), rm_c(h2, 1)), rm_rep0(x.z, rm_c(s, 2), rm_c(h2, 2)),
+                rm_rep0(x.w, rm_c(s, 3), rm_c(h2, 3)));
+}
 
 RM_HD vec2 clamp(const vec2& v, float lo, float hi) { return vec2(clamp(v.x, lo, hi), clamp(v.y, lo, hi)); }
 RM_HD vec3 clamp(const vec3& v, float lo, float hi) { return vec3(clamp(v.x, lo, hi), clamp(v.y, lo, hi), clamp(v.z, lo, hi)); }

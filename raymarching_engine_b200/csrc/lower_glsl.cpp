@@ -401,6 +401,104 @@ LowerResult lower_scene(const std::string& glsl, const std::set<std::string>& co
     }
     if (brace != 0) return fail(n ? T[n - 1].line : 1, "unexpected end of source: unbalanced '{'");
 
+    // ---- pass 2: domain-repetition idiom -----------------------------------------------------
+    // `mod(X + H1, S) - H2` -> rm_rep(X, H1, S, H2) and `mod(X, S) - H2` -> rm_rep0(X, S, H2), where the
+    // whole pattern is one operand of nothing tighter than the binary minus.  glsl_rt.h defines both
+    // helpers: the exact policy evaluates the expression exactly as written (same operations, same
+    // order), the fast policy turns a centred cell (H2 == S/2) into a centred remainder.
+    {
+        auto live = [&](size_t k) { return k < n && !T[k].drop && T[k].kind != kPP; };
+        auto next_live = [&](size_t k) { k++; while (k < n && !live(k)) k++; return k; };
+        auto prev_live = [&](size_t k) -> size_t { while (k > 0) { k--; if (live(k)) return k; } return n; };
+        auto match_close = [&](size_t open) -> size_t {   // index of the ')' / ']' matching T[open]
+            int d = 0;
+            for (size_t k = open; k < n; k++) {
+                if (!live(k)) continue;
+                if (T[k].text == "(" || T[k].text == "[") d++;
+                else if (T[k].text == ")" || T[k].text == "]") { d--; if (d == 0) return k; }
+            }
+            return n;
+        };
+        // primary: number | identifier [call] | parenthesised, each followed by .swizzle / [index]
+        auto parse_primary = [&](size_t k) -> size_t {   // returns index of the last token, or n
+            if (!live(k)) return n;
+            size_t last;
+            if (T[k].kind == kNumber) last = k;
+            else if (T[k].kind == kIdent) {
+                last = k;
+                size_t q = next_live(k);
+                if (q < n && T[q].text == "(") { last = match_close(q); if (last == n) return n; }
+            } else if (T[k].text == "(") { last = match_close(k); if (last == n) return n; }
+            else return n;
+            for (;;) {
+                size_t q = next_live(last);
+                if (q < n && T[q].text == ".") { size_t f = next_live(q); if (f < n && T[f].kind == kIdent) { last = f; continue; } return n; }
+                if (q < n && T[q].text == "[") { size_t c = match_close(q); if (c == n) return n; last = c; continue; }
+                break;
+            }
+            return last;
+        };
+        static const std::set<std::string> ok_before = {"(", ",", "=", "return", "?", ":", ";", "{", "}", "+=", "-=", "*=", "/="};
+        static const std::set<std::string> low_prec = {"<", ">", "<=", ">=", "==", "!=", "&&", "||", "!=", "?", ":", "=", "&", "|", "^", "<<", ">>",
+                                                        "+=", "-=", "*=", "/="};
+        for (size_t m = 0; m < n; m++) {
+            if (!live(m) || T[m].kind != kIdent || T[m].text != "mod") continue;
+            size_t open = next_live(m);
+            if (open >= n || T[open].text != "(") continue;
+            size_t pv = prev_live(m);
+            if (pv != n && !ok_before.count(T[pv].text)) continue;
+            if (pv != n && T[pv].text == "(") {
+                // `f(mod(..) - h)` is fine, `(mod(..)) - h` is handled as written; but `x.f(mod` cannot occur in GLSL
+            }
+            size_t close = match_close(open);
+            if (close == n) continue;
+            // split the two arguments at the top-level comma
+            size_t comma = n; int d = 0; bool bad = false; int commas = 0;
+            size_t last_add = n;      // last top-level binary + or - of argument 1
+            for (size_t k = next_live(open); k < close; k = next_live(k)) {
+                const std::string& w = T[k].text;
+                if (w == "(" || w == "[") d++;
+                else if (w == ")" || w == "]") d--;
+                else if (d == 0 && w == ",") { commas++; if (comma == n) comma = k; }
+                else if (d == 0 && comma == n) {
+                    if (low_prec.count(w)) bad = true;
+                    if (w == "+" || w == "-") {
+                        size_t b = prev_live(k);
+                        bool binary = b != n && b != open && (T[b].kind == kIdent || T[b].kind == kNumber || T[b].text == ")" || T[b].text == "]");
+                        if (binary) last_add = k;
+                    }
+                } else if (d == 0 && comma != n && low_prec.count(w)) bad = true;
+            }
+            if (bad || commas != 1 || comma == n) continue;
+            if (last_add != n && T[last_add].text != "+") continue;
+            // what follows: `- H2` with H2 a multiplicative chain of primaries
+            size_t minus = next_live(close);
+            if (minus >= n || T[minus].text != "-") continue;
+            size_t h2_last = parse_primary(next_live(minus));
+            if (h2_last == n) continue;
+            for (;;) {
+                size_t q = next_live(h2_last);
+                if (q < n && (T[q].text == "*" || T[q].text == "/")) {
+                    size_t e = parse_primary(next_live(q));
+                    if (e == n) { h2_last = n; break; }
+                    h2_last = e;
+                    continue;
+                }
+                break;
+            }
+            if (h2_last == n) continue;
+            {   // the operand after H2 must not bind tighter than '-'
+                size_t q = next_live(h2_last);
+                if (q < n && (T[q].text == "%" || T[q].text == "." || T[q].text == "[" || T[q].text == "(")) continue;
+            }
+            if (last_add != n) { T[m].text = "rm_rep"; T[last_add].text = ","; }
+            else T[m].text = "rm_rep0";
+            T[close].text = ",";
+            T[minus].drop = true;
+            T[h2_last].text += ")";
+        }
+    }
+
     // ---- emit -------------------------------------------------------------------------------
     std::string out;
     out.reserve(glsl.size() + 256);

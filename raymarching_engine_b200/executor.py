@@ -168,6 +168,22 @@ class RenderJobContext:                  # RenderJobExecutor.tsx:32-54
             raise RuntimeError(self.last_error())
         return rgba, depth
 
+    def present_async(self, fb: FramebufferInfo, brightness: float, want_depth: bool = True, slot: int = 0):
+        """Non-blocking present (rmb_present_async): display pass on the context's stream, readback on
+        the copy stream into the pinned buffers of ring slot `slot`.  Returns the (rgba8, depth) views,
+        valid after present_wait(fb)."""
+        rgba = self._pinned(("rgba", slot), (fb.local_rows, fb.width, 4), np.uint8)
+        depth = self._pinned(("depth", slot), (fb.local_rows, fb.width), np.float32) if want_depth else None
+        st = L.rmb_present_async(self.handle, fb.handle, float(np.float32(brightness)), rgba.ctypes.data_as(C.c_void_p),
+                                 depth.ctypes.data_as(C.c_void_p) if want_depth else None)
+        if st != _lib.RMB_OK:
+            raise RuntimeError(self.last_error())
+        return rgba, depth
+
+    def present_wait(self, fb: FramebufferInfo) -> None:
+        if L.rmb_present_wait(self.handle, fb.handle) != _lib.RMB_OK:
+            raise RuntimeError(self.last_error())
+
     def measure_fp32_peak(self, seconds: float = 0.5) -> float:
         out = C.c_double(0.0)
         if L.rmb_measure_fp32_peak(self.handle, seconds, C.byref(out)) != _lib.RMB_OK:
@@ -309,17 +325,24 @@ def do_render_job(schema: RenderJobSchema, context: RenderJobContext):
 
 
 def make_presenter(samples_up_to_this_point: int, sink: Optional[dict] = None, want_depth: bool = True,
-                   readback: str = "always") -> PresentFn:
+                   readback: str = "always", slot: int = 0) -> PresentFn:
     """makePresenter (index.tsx:25-59): display pass with brightness = 1 / samplesUpToThisPoint (the
     host's own counter; the generator's samplesSoFar argument is ignored for the brightness, as in
     the reference).  The canvas is replaced by `sink`: the latest frame lands in sink["rgba8"],
     sink["depth"] (views of pinned buffers).  readback="final" copies to the host only on the last
-    present of a job (the intermediate presents still run the display pass, like canvas redraws)."""
+    present of a job (the intermediate presents still run the display pass, like canvas redraws).
+    readback="async" does the same without blocking (present_async into pinned ring slot `slot`); the
+    caller waits with context.present_wait(sink["framebuffers"])."""
     def present(context: RenderJobContext, schema: RenderJobSchema, framebuffers: FramebufferInfo, samples_so_far: int) -> None:
         brightness = 1 / samples_up_to_this_point if samples_up_to_this_point else math.inf
         total = schema.render.samplesPerPixel * schema.render.subdivisions ** 2
         rb = readback == "always" or samples_so_far >= total
-        rgba, depth = context.present(framebuffers, brightness, want_depth, readback=rb)
+        if readback == "async" and rb:
+            rgba, depth = context.present_async(framebuffers, brightness, want_depth, slot)
+            if sink is not None:
+                sink["framebuffers"] = framebuffers
+        else:
+            rgba, depth = context.present(framebuffers, brightness, want_depth, readback=rb)
         if sink is not None:
             if rb:
                 sink["rgba8"], sink["depth"] = rgba, depth
@@ -342,3 +365,40 @@ def run_job(schema: RenderJobSchema, context: RenderJobContext, samples_up_to_th
     out = dict(result or {"success": False, "why": _gen_err("generator ended without a result")})
     out.update(sink)
     return out
+
+
+def render_frames(schemas, context: RenderJobContext, depth: int = 2, want_depth: bool = True):
+    """Pipelined pump for a sequence of jobs (a camera path, BASELINE.json config 5): every job runs
+    through do_render_job exactly like run_job, but its final present is non-blocking and the result
+    is handed out `depth - 1` jobs later, so the device->host readback of frame k overlaps the kernels
+    of frame k+1.  Yields (index, result dict) in order; result["rgba8"] / ["depth"] are views of a
+    pinned ring buffer that stay valid until `depth` more frames have been rendered."""
+    schemas = list(schemas)
+    pending = []      # (index, result, fb)
+    for k, schema in enumerate(schemas):
+        if k + 1 < len(schemas):
+            nxt = schemas[k + 1].render
+            # acquire the next job's framebuffer set before this job releases its own, so that two
+            # sets alternate and a set is never redrawn while it is being read back
+            context.fbo.create(nxt.width, nxt.height, nxt.frameid)
+        sink: dict = {}
+        n = schema.render.samplesPerPixel * schema.render.subdivisions ** 2
+        gen = do_render_job(schema, context)(make_presenter(n, sink, want_depth, readback="async", slot=k % depth))
+        result = None
+        try:
+            while True:
+                next(gen)
+        except StopIteration as stop:
+            result = dict(stop.value or {"success": False, "why": _gen_err("generator ended without a result")})
+        fb = sink.pop("framebuffers", None)
+        result.update(sink)
+        pending.append((k, result, fb))
+        while len(pending) >= depth:
+            i, res, f = pending.pop(0)
+            if f is not None:
+                context.present_wait(f)
+            yield i, res
+    for i, res, f in pending:
+        if f is not None:
+            context.present_wait(f)
+        yield i, res

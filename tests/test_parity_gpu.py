@@ -242,3 +242,75 @@ def test_row_tile_sharding_reassembles(ctx):
                 c.close()
         np.testing.assert_array_equal(full, want)
         np.testing.assert_array_equal(depth.view(np.uint32), acc.depth.view(np.uint32))
+
+
+def test_render_frames_pipelined_equals_run_job(ctx):
+    """The pipelined pump (non-blocking present, two alternating framebuffer sets, readback on the copy
+    stream) returns the same bytes as one blocking run_job per frame."""
+    import math
+    def schemas(base):
+        out = []
+        for k in range(5):
+            s = _schema("guide", 160, 90, "preview", frameid=base + k)
+            th = 0.4 * k
+            s.camera.position = (10.0 * math.sin(th), 0.0, 10.0 - 10.0 * math.cos(th))
+            c, sn = math.cos(-th), math.sin(-th)
+            s.camera.rotation = (c, 0, -sn, 0, 0, 1, 0, 0, sn, 0, c, 0, 0, 0, 0, 1)
+            out.append(s)
+        return out
+    rm.reset_halton()
+    want = []
+    for s in schemas(9100):
+        r = rm.run_job(s, ctx)
+        assert r["success"]
+        want.append((r["rgba8"].copy(), r["depth"].copy()))
+    rm.reset_halton()
+    n = 0
+    for i, r in rm.render_frames(schemas(9200), ctx, depth=2):
+        assert r["success"] and i == n
+        np.testing.assert_array_equal(r["rgba8"], want[i][0])
+        np.testing.assert_array_equal(r["depth"].view(np.uint32), want[i][1].view(np.uint32))
+        n += 1
+    assert n == 5
+
+
+def test_lazy_clear_partial_scissor_on_fresh_frame(ctx):
+    """A fresh framebuffer set drawn through a partial scissor must read as zero outside the scissor
+    (the clear is issued lazily; a full-frame draw skips it and tells the kernel prev == 0)."""
+    s = _schema("guide", 64, 48, "preview")
+    prog = ctx.program_cache.get_program(s.sdfShaderSource, None, dict(s.customShaderParameters))
+    fid = 9300
+    fb = ctx.fbo.create(64, 48, fid)
+    fb.write("color", np.full((48, 64, 4), 7.0, np.float32))
+    ctx.fbo.delete(64, 48, fid)
+    fb2 = ctx.fbo.create(64, 48, fid + 1)          # same set from purgatory, new frameid -> logically cleared
+    assert fb2.handle == fb.handle
+    rm.upload_sample_uniforms(prog, s, (0.5, 1.0 / 3.0))
+    assert rm._lib.lib.rmb_render_sample(ctx.handle, prog.handle, fb2.handle, 8, 8, 16, 16) == 0
+    col = fb2.read("color")
+    inside = np.zeros((48, 64), bool)
+    inside[8:24, 8:24] = True
+    assert np.all(col[~inside] == 0.0)
+    assert np.any(col[inside] != 0.0)
+    ctx.fbo.delete(64, 48, fid + 1)
+
+
+def test_rep_idiom_scenes_fast_close_to_exact(ctx):
+    """Scenes that use the domain-repetition idiom (lowered to rm_rep / rm_rep0): the fast flavour's
+    centred remainder stays within tolerance of the exact flavour on the SDF itself."""
+    rng = np.random.default_rng(11)
+    pts = rng.uniform(-8, 8, (4000, 3)).astype(np.float32)
+    pts[:, 2] += 8.0
+    for name in ("guide", "fractal1", "menger-sponge", "sphere-grid", "inline-default"):
+        src = scene_source(name)
+        custom = rm.default_custom_settings(src)
+        vals = []
+        for fl in (rm.FLAVOUR_EXACT, rm.FLAVOUR_FAST):
+            prog = ctx.program_cache.get_program(src, fl, custom)
+            assert isinstance(prog, rm.Program), prog
+            assert "rm_rep" in prog.source()
+            out = np.zeros((len(pts), 17), np.float32)
+            assert rm._lib.lib.rmb_probe(ctx.handle, prog.handle, pts.ctypes.data_as(C.c_void_p), len(pts), out.ctypes.data_as(C.c_void_p)) == 0
+            vals.append(out[:, 15].copy())
+        err = np.abs(vals[0] - vals[1])
+        assert float(err.max()) < 2e-5, (name, float(err.max()))

@@ -1,0 +1,70 @@
+#!/usr/bin/env python3
+"""Full-size tolerance report (runs on the GPU box): renders the default scene at WxH in preview and
+full mode with the exact and the fast flavour, checks the exact flavour against the CPU oracle (bit
+for bit) and measures the fast flavour against it with the north_star tolerance (RGBA8 within 1/255
+on >= 99.9 % of pixels, hit depth within 1e-4 relative).  Writes one JSON object to stdout."""
+import argparse
+import json
+import sys
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "oracle"))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--width", type=int, default=1920)
+    ap.add_argument("--height", type=int, default=1080)
+    ap.add_argument("--poses", type=int, nargs="*", default=[0, 40])
+    ap.add_argument("--oracle", action="store_true", help="also render with the CPU oracle (slow)")
+    ap.add_argument("--modes", nargs="*", default=["preview", "full"])
+    args = ap.parse_args()
+    import raymarching_engine_b200 as rm
+    import bench
+    src = (ROOT / "scenes" / "guide.glsl").read_text()
+    custom = rm.default_custom_settings(src)
+    ctxs = {"exact": rm.load_render_job_context(device=0, flavour=rm.FLAVOUR_EXACT), "fast": rm.load_render_job_context(device=0, flavour=rm.FLAVOUR_FAST)}
+    report = {"width": args.width, "height": args.height, "cases": []}
+    fid = 1
+    for mode in args.modes:
+        for pose in args.poses:
+            got = {}
+            for fl, ctx in ctxs.items():
+                fid += 1
+                s = bench.make_schema(rm, src, custom, args.width, args.height, mode, pose, fid)
+                rm.reset_halton()
+                r = rm.run_job(s, ctx)
+                assert r["success"], r["why"]
+                got[fl] = (r["rgba8"].copy(), r["depth"].copy())
+            case = {"mode": mode, "pose": pose}
+            a, b = got["exact"], got["fast"]
+            diff = np.abs(a[0].astype(np.int32) - b[0].astype(np.int32)).max(axis=2)
+            case["fast_vs_exact_rgba8_within_1"] = float((diff <= 1).mean())
+            case["fast_vs_exact_rgba8_identical"] = float((diff == 0).mean())
+            hit = np.isfinite(a[1]) & (a[1] < 1e3) & (a[1] > 0)
+            rel = np.abs(a[1] - b[1]) / np.maximum(np.abs(a[1]), 1e-30)
+            case["hit_fraction"] = float(hit.mean())
+            case["fast_vs_exact_hit_depth_within_1e-4"] = float((rel[hit] <= 1e-4).mean()) if hit.any() else 1.0
+            case["fast_vs_exact_depth_within_1e-4_all_px"] = float((rel <= 1e-4).mean())
+            if args.oracle:
+                import pyoracle
+                s = bench.make_schema(rm, src, custom, args.width, args.height, mode, pose, 1)
+                rm.reset_halton()
+                t0 = time.perf_counter()
+                acc, want = pyoracle.run_job("guide", s)
+                case["oracle_seconds"] = time.perf_counter() - t0
+                case["exact_vs_oracle_rgba8_identical"] = bool(np.array_equal(a[0], want))
+                case["exact_vs_oracle_depth_identical"] = bool(np.array_equal(a[1].view(np.uint32), acc.depth.view(np.uint32)))
+                d2 = np.abs(b[0].astype(np.int32) - want.astype(np.int32)).max(axis=2)
+                case["fast_vs_oracle_rgba8_within_1"] = float((d2 <= 1).mean())
+            report["cases"].append(case)
+    print(json.dumps(report, indent=1))
+
+
+if __name__ == "__main__":
+    main()
