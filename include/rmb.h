@@ -71,6 +71,12 @@ int rmb_abi_version(void);
 rmb_ctx* rmb_ctx_create(int device, int rank, int n_ranks, int tile_rows);
 void rmb_ctx_destroy(rmb_ctx* ctx);
 const char* rmb_last_error(rmb_ctx* ctx);
+/* Draw pipeline: 0 (default) = wavefront kernels (setup -> persistent march -> shade) whenever the
+ * scene's code is free of per-invocation mutable state, 1 = one-thread-per-pixel megakernel always.
+ * Both produce identical accumulators in the exact flavour (tests cross-check them). */
+rmb_status rmb_ctx_set_pipeline(rmb_ctx* ctx, int pipeline);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+uint64_t rmb_ctx_launch_count(rmb_ctx* ctx);
 /* cudaStream_t all work of this context is enqueued on (for CUDA-event timing by the caller) */
 void* rmb_ctx_stream(rmb_ctx* ctx);
 rmb_status rmb_sync(rmb_ctx* ctx);
@@ -91,7 +97,8 @@ rmb_status rmb_program_get(rmb_ctx* ctx, const char* scene_glsl, size_t scene_le
                            char* err_type, char* infolog, size_t infolog_cap);
 /* generated CUDA C++ translation unit (debugging / tests); owned by the program */
 const char* rmb_program_source(rmb_program* prog);
-/* registers per thread / local-memory bytes of the kernels (0 preview, 1 full); -1 if unknown */
+/* registers per thread / local-memory bytes of a kernel: 0 preview megakernel, 1 full megakernel,
+ * 2 preview march, 3 castRay march, 4 setup, 5 bounce (2..5: wavefront, pure scenes only); -1 if unknown */
 int rmb_program_kernel_attr(rmb_program* prog, int kernel, int* regs, int* local_bytes);
 
 /* ---- uniforms ------------------------------------------------------------------------------

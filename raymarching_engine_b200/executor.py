@@ -131,6 +131,9 @@ class RenderJobContext:                  # RenderJobExecutor.tsx:32-54
     def sync(self) -> None:
         L.rmb_sync(self.handle)
 
+    def launch_count(self) -> int:
+        return int(L.rmb_ctx_launch_count(self.handle))
+
     def counters(self, reset: bool = False):
         out = (C.c_uint64 * 2)()
         L.rmb_counters_read(self.handle, out, 1 if reset else 0)
@@ -200,12 +203,16 @@ class RenderJobContext:                  # RenderJobExecutor.tsx:32-54
 
 
 def load_render_job_context(device: int = 0, rank: int = 0, n_ranks: int = 1, tile_rows: int = 16,
-                            flavour: int = _lib.FLAVOUR_EXACT, specialize: bool = True) -> Optional[RenderJobContext]:
+                            flavour: int = _lib.FLAVOUR_EXACT, specialize: bool = True,
+                            pipeline: str = "wavefront") -> Optional[RenderJobContext]:
     """loadRenderJobContext(gl) (LoadRenderJobContext.tsx:268-287): returns None when any piece
     of the context cannot be created (the reference returns undefined)."""
     h = L.rmb_ctx_create(device, rank, n_ranks, tile_rows)
     if not h:
         return None
+    # "wavefront": setup -> persistent march -> shade kernels when the scene allows it (default);
+    # "megakernel": one thread per pixel always
+    L.rmb_ctx_set_pipeline(h, {"wavefront": 0, "megakernel": 1}[pipeline])
     return RenderJobContext(h, device, rank, n_ranks, tile_rows, flavour, specialize)
 
 

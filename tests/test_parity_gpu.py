@@ -314,3 +314,58 @@ def test_rep_idiom_scenes_fast_close_to_exact(ctx):
             vals.append(out[:, 15].copy())
         err = np.abs(vals[0] - vals[1])
         assert float(err.max()) < 2e-5, (name, float(err.max()))
+
+
+@pytest.mark.parametrize("mode,lights,size", [("preview", 0, (333, 187)), ("full", 1, (160, 90)), ("full", 2, (101, 57))])
+def test_wavefront_equals_megakernel(ctx, mode, lights, size):
+    """The wavefront pipeline (setup -> persistent march with lane refill -> shade) and the
+    one-thread-per-pixel megakernel produce bit-identical accumulators (exact flavour), including
+    frame sizes that are not multiples of the 8x4 ray tiles."""
+    mega = rm.load_render_job_context(device=0, pipeline="megakernel")
+    try:
+        outs = []
+        for c in (ctx, mega):
+            s = _schema("guide", size[0], size[1], mode, lights=lights, samplesPerPixel=2)
+            if lights > 1:
+                s.lights[1].position = (1.0, 2.0, 3.0)
+                s.lights[1].size = 0.3
+            _FRAME[0] += 1
+            s.render.frameid = _FRAME[0]
+            rm.reset_halton()
+            c.counters(reset=True)
+            fb = c.fbo.create(s.render.width, s.render.height, s.render.frameid)
+            got = rm.run_job(s, c)
+            assert got["success"], got["why"]
+            outs.append({p: fb.read(p) for p in ("color", "normalAndDofRadius", "albedoAndDepth", "depth")} | {"rgba8": got["rgba8"].copy(), "evals": c.counters(reset=True)})
+        a, b = outs
+        np.testing.assert_array_equal(a["color"].view(np.uint32), b["color"].view(np.uint32))
+        np.testing.assert_array_equal(a["normalAndDofRadius"], b["normalAndDofRadius"])
+        np.testing.assert_array_equal(a["albedoAndDepth"], b["albedoAndDepth"])
+        np.testing.assert_array_equal(a["depth"].view(np.uint32), b["depth"].view(np.uint32))
+        np.testing.assert_array_equal(a["rgba8"], b["rgba8"])
+        assert a["evals"][1] == b["evals"][1] == 2 * size[0] * size[1]
+        assert a["evals"][0] == b["evals"][0]
+    finally:
+        mega.close()
+
+
+IMPURE_SCENE = """
+float wobble = 0.0;
+float sdf(vec3 p) {
+  wobble += 0.001;
+  return length(p - vec3(0.0, 0.0, 4.0)) - 1.0 - wobble;
+}
+"""
+
+
+def test_impure_scene_uses_megakernel(ctx):
+    """A scene with mutable global state cannot use the fixed-point exit or the wavefront pipeline
+    (an SDF call is not a pure function of the position): it renders through the megakernel and
+    executes exactly steps[0] evaluations per pixel."""
+    ctx.counters(reset=True)
+    s = rm.default_schema(IMPURE_SCENE, {}, width=64, height=32, renderMode="preview", frameid=9400)
+    r = rm.run_job(s, ctx)
+    assert r["success"], r["why"]
+    evals, px = ctx.counters(reset=True)
+    assert px == 64 * 32 and evals == 64 * 32 * 128
+    assert r["rgba8"].shape == (32, 64, 4) and r["rgba8"][..., 3].min() == 255
