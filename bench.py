@@ -177,9 +177,10 @@ def metric_name(args) -> str:
 def workload_config(args) -> dict:
     return {"workload": f"guide.glsl default scene, {args.width}x{args.height}, {args.mode} mode, 1 spp/frame, "
                         f"256-pose orbit camera path (pose 0 = reference start-up view), fresh framebuffer per frame",
-            "flavour": args.flavour, "shard": args.shard if args.gpus > 1 else "none",
-            "l2": "flushed between steps (256 MiB device memset on the stream, outside the per-step event pair); "
-                  "e2e alternates two framebuffer sets (2 x 40 B/px) and reads every frame back",
+            "flavour": args.flavour, "pipeline": args.pipeline, "shard": args.shard if args.gpus > 1 else "none",
+            "contexts_per_gpu": 1 if (args.gpus > 1 and args.shard == "tiles") else args.contexts,
+            "l2": "flushed before every step (256 MiB in-stream device memset, inside the timed region); "
+                  "e2e alternates two framebuffer sets per context (40 B/px each) and reads every frame back",
             "steps_per_px_reference": ref_steps_per_px(args)}
 
 
@@ -194,54 +195,48 @@ def run_b200(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
     dist = None
     if world > 1:
         import torch.distributed as dist_mod
         dist = dist_mod
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.init_process_group("nccl", device_id=dev)
     W, H = args.width, args.height
     flavour = rm.FLAVOUR_FAST if args.flavour == "fast" else rm.FLAVOUR_EXACT
     tiles = world > 1 and args.shard == "tiles"
-    ctx = rm.load_render_job_context(device=local, rank=rank if tiles else 0, n_ranks=world if tiles else 1, tile_rows=16, flavour=flavour)
-    if ctx is None:
-        raise SystemExit("bench.py: " + rm.context_error())
+    # Frames of the path are independent, so they are dealt round-robin to `--contexts` contexts of
+    # this GPU (each its own stream, module instance and ray planes): the drain phase of one frame's
+    # persistent march kernel overlaps the next frame's kernels.
+    nctx = 1 if tiles else max(1, args.contexts)
+    ctxs = []
+    for _ in range(nctx):
+        c = rm.load_render_job_context(device=local, rank=rank if tiles else 0, n_ranks=world if tiles else 1, tile_rows=16,
+                                       flavour=flavour, pipeline=args.pipeline)
+        if c is None:
+            raise SystemExit("bench.py: " + rm.context_error())
+        ctxs.append(c)
     src = (ROOT / "scenes" / "guide.glsl").read_text()
     custom = rm.default_custom_settings(src)
-    stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local))
-    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    streams = [torch.cuda.ExternalStream(c.stream(), device=dev) for c in ctxs]
+    flush_bufs = [torch.empty(256 << 20, dtype=torch.uint8, device="cuda") for _ in ctxs]
     L = rm._lib.lib
-
-    prog = ctx.program_cache.get_program(src, None, custom)
-    if not isinstance(prog, rm.Program):
-        raise SystemExit("bench.py: program failed to compile: " + prog.infoLog)
-    regs = prog.kernel_attr(0 if args.mode == "preview" else 1)
+    progs = []
+    for c in ctxs:
+        prog = c.program_cache.get_program(src, None, custom)
+        if not isinstance(prog, rm.Program):
+            raise SystemExit("bench.py: program failed to compile: " + prog.infoLog)
+        progs.append(prog)
+    wavefront = args.pipeline == "wavefront"
+    regs = progs[0].kernel_attr((2 if args.mode == "preview" else 3) if wavefront else (0 if args.mode == "preview" else 1))
 
     frame_counter = [1]
 
     def pose_of(step):   # weak scaling: rank r renders poses r, r+world, ...; tiles: everyone renders pose `step`
         return step if tiles else step * world + rank
 
-    def device_step(step, ev=None):
-        """one frame, everything resident in HBM; returns nothing (async)"""
-        frame_counter[0] += 1
-        s = make_schema(rm, src, custom, W, H, args.mode, pose_of(step), frame_counter[0])
-        fb = ctx.fbo.create(W, H, s.render.frameid)
-        rm.upload_sample_uniforms(prog, s, (0.5, 1.0 / 3.0))
-        if ev:
-            ev[0].record(stream)
-        st = L.rmb_render_sample(ctx.handle, prog.handle, fb.handle, 0, 0, W, H)
-        if ev:
-            ev[1].record(stream)
-        assert st == 0, ctx.last_error()
-        st = L.rmb_present_device(ctx.handle, fb.handle, 1.0)
-        assert st == 0, ctx.last_error()
-        if tiles:
-            gather_tiles(fb)
-        ctx.fbo.delete(W, H, s.render.frameid)
-
     gather_state = {}
 
-    def gather_tiles(fb):
+    def gather_tiles(ctx, stream, fb):
         # NCCL gather of each rank's RGBA8 rows to rank 0 (SURVEY.md 8e): equal-sized padded
         # buffers (ranks own 1..2 tiles more or less), issued in the library's stream order
         if "send" not in gather_state:
@@ -254,40 +249,64 @@ def run_b200(args):
         with torch.cuda.stream(stream):
             dist.gather(gather_state["send"], gather_state["recv"], dst=0)
 
+    def device_step(step, flush=False):
+        """one frame, everything resident in HBM (async): [L2 flush], uniforms, raymarch, display[, gather]"""
+        k = step % nctx
+        ctx, prog, stream = ctxs[k], progs[k], streams[k]
+        if flush:
+            with torch.cuda.stream(stream):
+                flush_bufs[k].zero_()
+        frame_counter[0] += 1
+        s = make_schema(rm, src, custom, W, H, args.mode, pose_of(step), frame_counter[0])
+        fb = ctx.fbo.create(W, H, s.render.frameid)
+        rm.upload_sample_uniforms(prog, s, (0.5, 1.0 / 3.0))
+        st = L.rmb_render_sample(ctx.handle, prog.handle, fb.handle, 0, 0, W, H)
+        assert st == 0, ctx.last_error()
+        st = L.rmb_present_device(ctx.handle, fb.handle, 1.0)
+        assert st == 0, ctx.last_error()
+        if tiles:
+            gather_tiles(ctx, stream, fb)
+        ctx.fbo.delete(W, H, s.render.frameid)
+
     def barrier():
         if dist:
             dist.barrier()
         torch.cuda.synchronize()
 
     # ---- warm-up (also compiles the program variant) ----
-    for i in range(max(args.warmup, 3)):
+    for i in range(max(args.warmup, 3) * nctx):
         device_step(i)
-    ctx.sync()
-    ctx.counters(reset=True)
+    for c in ctxs:
+        c.sync()
+        c.counters(reset=True)
 
     sampler = ClockSampler(local)
     sampler.start()
 
     # ---- timed: device-resident.  All K steps are enqueued back to back (the host runs ahead of the
-    # GPU); each step is bracketed by its own CUDA events on the library's stream with the untimed L2
-    # flush between steps, so the sum of the K intervals is pure device time of the K steps.
-    events = []
+    # GPU), each preceded by an in-stream 256 MiB L2 flush that is INSIDE the timed region.  The region
+    # runs from one start event (GPU idle, recorded on every stream) to the last end event.
     barrier()
+    for c in ctxs:
+        c.timing(True)
+    launches0 = sum(c.launch_count() for c in ctxs)
+    starts = [torch.cuda.Event(enable_timing=True) for _ in ctxs]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in ctxs]
+    for e, st_ in zip(starts, streams):
+        e.record(st_)
     for i in range(args.steps):
-        with torch.cuda.stream(stream):
-            flush_buf.zero_()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        device_step(args.warmup + i, (k0, k1))
-        e1.record(stream)
-        events.append((e0, e1, k0, k1))
+        device_step(args.warmup + i, flush=True)
+    for e, st_ in zip(ends, streams):
+        e.record(st_)
     barrier()
-    ctx.sync()
-    step_ms = [e0.elapsed_time(e1) for e0, e1, _, _ in events]
-    kern_ms = [k0.elapsed_time(k1) for _, _, k0, k1 in events]
-    evals, pxs = ctx.counters(reset=True)
-    total_ms = sum(step_ms)
+    for c in ctxs:
+        c.sync()
+    gpu_launches = sum(c.launch_count() for c in ctxs) - launches0
+    hot = [c.timing(False) for c in ctxs]
+    hot_ms, hot_launches = sum(h[0] for h in hot), sum(h[1] for h in hot)
+    total_ms = max(starts[0].elapsed_time(e) for e in ends)
+    cnt = [c.counters(reset=True) for c in ctxs]
+    evals, pxs = sum(x[0] for x in cnt), sum(x[1] for x in cnt)
     if dist:
         t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -306,11 +325,11 @@ def run_b200(args):
         return out
 
     checksum = 0
-    for _i, res in rm.render_frames(e2e_schemas(0, 3), ctx):
+    for _i, res in rm.render_frames(e2e_schemas(0, 2 * nctx + 1), ctxs):
         assert res["success"], res["why"]
     barrier()
     t0 = time.perf_counter()
-    for _i, res in rm.render_frames(e2e_schemas(args.warmup, args.steps), ctx):
+    for _i, res in rm.render_frames(e2e_schemas(args.warmup, args.steps), ctxs):
         assert res["success"], res["why"]
         checksum += int(res["rgba8"][0, 0, 0]) + int(res["rgba8"][-1, -1, 3])   # the host reads the result
     torch.cuda.synchronize()
@@ -323,21 +342,35 @@ def run_b200(args):
     e2e_value = frames * W * H / e2e_s / 1e6
     clocks = sampler.stop()
 
-    # ---- roofline of the raymarch kernel ----
-    fp32_measured = ctx.measure_fp32_peak(0.5)
+    # ---- roofline of the hot kernel (the persistent march kernel) ----
+    fp32_measured = ctxs[0].measure_fp32_peak(0.5)
     sm_count = torch.cuda.get_device_properties(local).multi_processor_count
     sm_max = clocks.get("sm_max_mhz") or 1965.0
     nominal_peak = sm_count * 128 * 2 * sm_max * 1e6 / 1e12
     flop_per_step = FLOP_PER_PREVIEW_STEP if args.mode == "preview" else FLOP_PER_CASTRAY_STEP
-    kernel_s = sum(kern_ms) * 1e-3
+    kernel_s = hot_ms * 1e-3
+    # with several contexts the hot kernels of different frames overlap each other's drain phase, so
+    # the sum of their individual durations can exceed their share of the wall time
     achieved = evals * flop_per_step / kernel_s / 1e12 if kernel_s > 0 else 0.0
+    if wavefront:
+        hot_kernel = "rm_wf_march_preview_kernel" if args.mode == "preview" else "rm_wf_march_cast_kernel"
+    else:
+        hot_kernel = "rm_preview_kernel" if args.mode == "preview" else "rm_full_kernel"
+    traffic = None
+    try:
+        tj = json.loads((ROOT / "profiles" / "traffic.json").read_text())
+        traffic = tj.get(f"{hot_kernel}:{W}x{H}:{args.flavour}")
+    except (OSError, ValueError):
+        pass
     roofline = {
-        "bound": "fp32", "achieved": achieved, "peak": nominal_peak, "unit": "TFLOP/s", "frac": achieved / nominal_peak, "traffic": None,
+        "bound": "fp32", "achieved": achieved, "peak": nominal_peak, "unit": "TFLOP/s", "frac": achieved / nominal_peak, "traffic": traffic,
         "peak_source": f"derived: {sm_count} SMs x 128 FP32 lanes x 2 x {sm_max:.0f} MHz (MEASURED_PEAKS.json has no FP32 figure; BASELINE.md section 2)",
         "peak_measured_ffma": fp32_measured, "frac_of_measured_ffma": achieved / fp32_measured if fp32_measured else None,
-        "kernel": "rm_preview_kernel" if args.mode == "preview" else "rm_full_kernel",
-        "kernel_ms_avg": 1e3 * kernel_s / max(args.steps, 1), "kernel_share_of_step": kernel_s / (sum(step_ms) * 1e-3),
-        "executed_sdf_evals_per_launch": evals / max(args.steps, 1), "flop_per_step": flop_per_step,
+        "kernel": hot_kernel, "kernel_launches_per_step": hot_launches / max(args.steps, 1),
+        "kernel_ms_per_step": 1e3 * kernel_s / max(args.steps, 1), "kernel_ms_avg": 1e3 * kernel_s / max(hot_launches, 1),
+        "kernel_share_of_step": kernel_s / (total_ms * 1e-3),
+        "whole_step_frac": (evals * flop_per_step / (total_ms * 1e-3) / 1e12) / nominal_peak,
+        "executed_sdf_evals_per_step": evals / max(args.steps, 1), "flop_per_step": flop_per_step,
         "executed_steps_per_px": evals / max(pxs, 1), "registers_per_thread": regs[0], "local_bytes": regs[1],
     }
 
@@ -348,9 +381,10 @@ def run_b200(args):
         "roofline": roofline,
         "e2e": {"value": e2e_value, "unit": "Mpx/s", "h2d_bytes_per_step": 712, "d2h_bytes_per_step": W * H * 8,
                 "ms_per_step": 1e3 * e2e_s / max(args.steps, 1)},
-        "gpu_launches": 2 * args.steps,   # rm_*_kernel + rm_display_kernel per step (device-resident loop)
+        "gpu_launches": gpu_launches,   # counted by the library: every kernel it launched in the device-resident timed loop
         "clocks": clocks,
-        "extra": {"msteps_per_s_ref_equiv": value * ref_steps_per_px(args), "e2e_msteps_per_s_ref_equiv": e2e_value * ref_steps_per_px(args)},
+        "extra": {"msteps_per_s_ref_equiv": value * ref_steps_per_px(args), "e2e_msteps_per_s_ref_equiv": e2e_value * ref_steps_per_px(args),
+                  "msteps_per_s_executed": evals / (total_ms * 1e-3) / 1e6 * (world if not tiles else 1)},
     }
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -358,7 +392,8 @@ def run_b200(args):
         line["cpu_baseline"] = {"value": mpx, "unit": "Mpx/s", "cores": cores, "kind": "port", "sample": desc, "seconds": secs}
     if rank == 0:
         print(json.dumps(line), flush=True)
-    ctx.close()
+    for c in ctxs:
+        c.close()
     if dist:
         dist.destroy_process_group()
 
@@ -374,6 +409,8 @@ def main():
     ap.add_argument("--mode", default="preview", choices=["preview", "full"])
     ap.add_argument("--flavour", default="exact", choices=["exact", "fast"])
     ap.add_argument("--shard", default="poses", choices=["poses", "tiles"])
+    ap.add_argument("--pipeline", default="wavefront", choices=["wavefront", "megakernel"])
+    ap.add_argument("--contexts", type=int, default=2, help="contexts (streams) per GPU the independent frames are dealt to")
     ap.add_argument("--cpu-band-rows", type=int, default=360)
     ap.add_argument("--ref-band-rows", type=int, default=120)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -77,6 +77,10 @@ const char* rmb_last_error(rmb_ctx* ctx);
 rmb_status rmb_ctx_set_pipeline(rmb_ctx* ctx, int pipeline);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 uint64_t rmb_ctx_launch_count(rmb_ctx* ctx);
+/* Device timing of the hot kernel (the persistent march kernel of the wavefront pipeline, or the
+ * megakernel): returns the CUDA-event time and launch count accumulated since the previous call, then
+ * switches the collection on or off.  Synchronises the stream.  Used by bench.py's roofline. */
+rmb_status rmb_ctx_timing(rmb_ctx* ctx, int enable, double* hot_kernel_ms, uint64_t* hot_kernel_launches);
 /* cudaStream_t all work of this context is enqueued on (for CUDA-event timing by the caller) */
 void* rmb_ctx_stream(rmb_ctx* ctx);
 rmb_status rmb_sync(rmb_ctx* ctx);

@@ -19,7 +19,7 @@ UNIFORM_F, UNIFORM_I, UNIFORM_UI = 0, 1, 2
 
 # every symbol include/rmb.h declares; tests check that the library exports all of them
 EXPORTED_SYMBOLS = [
-    "rmb_abi_version", "rmb_ctx_create", "rmb_ctx_destroy", "rmb_last_error", "rmb_ctx_stream", "rmb_sync", "rmb_ctx_set_pipeline", "rmb_ctx_launch_count",
+    "rmb_abi_version", "rmb_ctx_create", "rmb_ctx_destroy", "rmb_last_error", "rmb_ctx_stream", "rmb_sync", "rmb_ctx_set_pipeline", "rmb_ctx_launch_count", "rmb_ctx_timing",
     "rmb_program_get", "rmb_program_source", "rmb_program_kernel_attr", "rmb_uniform_set", "rmb_uniform_set_array",
     "rmb_uniform_matrix4", "rmb_fb_acquire", "rmb_fb_release", "rmb_fb_local_rows", "rmb_fb_global_row",
     "rmb_render_sample", "rmb_present", "rmb_present_device", "rmb_present_async", "rmb_present_wait", "rmb_fb_device_ptr", "rmb_fb_plane_bytes",
@@ -53,6 +53,7 @@ def _load() -> C.CDLL:
         "rmb_sync": (i, [vp]),
         "rmb_ctx_set_pipeline": (i, [vp, i]),
         "rmb_ctx_launch_count": (C.c_uint64, [vp]),
+        "rmb_ctx_timing": (i, [vp, i, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
         "rmb_program_get": (i, [vp, cp, sz, i, C.POINTER(SpecUniform), i, C.POINTER(vp), cp, cp, sz]),
         "rmb_program_source": (cp, [vp]),
         "rmb_program_kernel_attr": (i, [vp, i, C.POINTER(i), C.POINTER(i)]),

@@ -74,12 +74,22 @@ RM_HD double trig_reduce(double x, int* quadrant) {
     const double PIO2_1 = 1.57079632673412561417e+00;   // first 33 bits of pi/2
     const double PIO2_2 = 6.07710050630396597660e-11;   // next 33 bits
     const double PIO2_2T = 2.02226624879595063154e-21;  // remainder
-    double k = drint(x * TWO_OVER_PI);
+    const double xs = x * TWO_OVER_PI;
+    double k;
+    if (dabs(xs) < 2147483648.0) {
+        // round-to-nearest-even by the 2^52+2^51 trick; the integer (two's complement) is then
+        // sitting in the low mantissa bits of t, so k mod 4 is a mask - no floor / conversion
+        const double M = 6755399441055744.0;
+        const double t = xs + M;
+        k = t - M;
+        *quadrant = (int)(d2ll(t) & 3);
+    } else {
+        k = drint(xs);
+        *quadrant = (int)dfma(-4.0, dfloor(k * 0.25), k);   // exact: k mod 4 in {0,1,2,3}
+    }
     double r = dfma(-k, PIO2_1, x);
     r = dfma(-k, PIO2_2, r);
     r = dfma(-k, PIO2_2T, r);
-    double q = dfma(-4.0, dfloor(k * 0.25), k);         // exact: k mod 4 in {0,1,2,3}
-    *quadrant = (int)q;
     return r;
 }
 

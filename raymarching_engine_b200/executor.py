@@ -131,6 +131,13 @@ class RenderJobContext:                  # RenderJobExecutor.tsx:32-54
     def sync(self) -> None:
         L.rmb_sync(self.handle)
 
+    def timing(self, enable: bool):
+        """(hot-kernel milliseconds, launches) accumulated since the last call; then turns collection on/off"""
+        ms, n = C.c_double(0.0), C.c_uint64(0)
+        if L.rmb_ctx_timing(self.handle, 1 if enable else 0, C.byref(ms), C.byref(n)) != _lib.RMB_OK:
+            raise RuntimeError(self.last_error())
+        return ms.value, int(n.value)
+
     def launch_count(self) -> int:
         return int(L.rmb_ctx_launch_count(self.handle))
 
@@ -374,23 +381,30 @@ def run_job(schema: RenderJobSchema, context: RenderJobContext, samples_up_to_th
     return out
 
 
-def render_frames(schemas, context: RenderJobContext, depth: int = 2, want_depth: bool = True):
+def render_frames(schemas, context, depth: int = 2, want_depth: bool = True):
     """Pipelined pump for a sequence of jobs (a camera path, BASELINE.json config 5): every job runs
     through do_render_job exactly like run_job, but its final present is non-blocking and the result
-    is handed out `depth - 1` jobs later, so the device->host readback of frame k overlaps the kernels
-    of frame k+1.  Yields (index, result dict) in order; result["rgba8"] / ["depth"] are views of a
-    pinned ring buffer that stay valid until `depth` more frames have been rendered."""
+    is handed out later, so the device->host readback of frame k overlaps the kernels of frame k+1.
+    `context` may be a list of contexts on the same device (each has its own stream, program modules
+    and scratch): frames are dealt round-robin, so that the drain phase of one frame's persistent
+    march kernel overlaps the next frame's kernels.  Yields (index, result dict) in order;
+    result["rgba8"] / ["depth"] are views of a pinned ring buffer that stay valid until
+    `depth * len(contexts)` more frames have been rendered."""
     schemas = list(schemas)
-    pending = []      # (index, result, fb)
+    contexts = list(context) if isinstance(context, (list, tuple)) else [context]
+    nctx = len(contexts)
+    window = depth * nctx
+    pending = []      # (index, result, context, fb)
     for k, schema in enumerate(schemas):
-        if k + 1 < len(schemas):
-            nxt = schemas[k + 1].render
-            # acquire the next job's framebuffer set before this job releases its own, so that two
+        ctx = contexts[k % nctx]
+        if k + nctx < len(schemas):
+            nxt = schemas[k + nctx].render
+            # acquire this context's next framebuffer set before this job releases its own, so that two
             # sets alternate and a set is never redrawn while it is being read back
-            context.fbo.create(nxt.width, nxt.height, nxt.frameid)
+            ctx.fbo.create(nxt.width, nxt.height, nxt.frameid)
         sink: dict = {}
         n = schema.render.samplesPerPixel * schema.render.subdivisions ** 2
-        gen = do_render_job(schema, context)(make_presenter(n, sink, want_depth, readback="async", slot=k % depth))
+        gen = do_render_job(schema, ctx)(make_presenter(n, sink, want_depth, readback="async", slot=(k // nctx) % depth))
         result = None
         try:
             while True:
@@ -399,13 +413,13 @@ def render_frames(schemas, context: RenderJobContext, depth: int = 2, want_depth
             result = dict(stop.value or {"success": False, "why": _gen_err("generator ended without a result")})
         fb = sink.pop("framebuffers", None)
         result.update(sink)
-        pending.append((k, result, fb))
-        while len(pending) >= depth:
-            i, res, f = pending.pop(0)
+        pending.append((k, result, ctx, fb))
+        while len(pending) >= window:
+            i, res, c, f = pending.pop(0)
             if f is not None:
-                context.present_wait(f)
+                c.present_wait(f)
             yield i, res
-    for i, res, f in pending:
+    for i, res, c, f in pending:
         if f is not None:
-            context.present_wait(f)
+            c.present_wait(f)
         yield i, res
