@@ -275,7 +275,7 @@ def run_b200(args):
 
     # ---- warm-up (also compiles the program variant) ----
     for i in range(max(args.warmup, 3) * nctx):
-        device_step(i)
+        device_step(i, flush=True)
     for c in ctxs:
         c.sync()
         c.counters(reset=True)

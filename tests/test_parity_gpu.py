@@ -369,3 +369,31 @@ def test_impure_scene_uses_megakernel(ctx):
     evals, px = ctx.counters(reset=True)
     assert px == 64 * 32 and evals == 64 * 32 * 128
     assert r["rgba8"].shape == (32, 64, 4) and r["rgba8"][..., 3].min() == 255
+
+
+def _golden_cases():
+    import sys
+    from pathlib import Path
+    sys.path.insert(0, str(Path(__file__).resolve().parent / "golden"))
+    import gen_golden
+    return gen_golden
+
+
+@pytest.mark.parametrize("name", sorted(_golden_cases().CASES))
+def test_golden_fixtures(ctx, name):
+    """CUDA path (C ABI, wavefront pipeline, exact flavour) against the committed golden vectors."""
+    from pathlib import Path
+    g = _golden_cases()
+    scene, s = g.make_case(rm, name)
+    _FRAME[0] += 1
+    s.render.frameid = _FRAME[0]
+    rm.reset_halton()
+    fb = ctx.fbo.create(s.render.width, s.render.height, s.render.frameid)
+    got = rm.run_job(s, ctx)
+    assert got["success"], got["why"]
+    want = np.load(Path(__file__).resolve().parent / "golden" / f"{name}.npz")
+    np.testing.assert_array_equal(got["rgba8"], want["rgba8"])
+    np.testing.assert_array_equal(fb.read("color").view(np.uint32), want["color"])
+    np.testing.assert_array_equal(fb.read("normalAndDofRadius"), want["nd"])
+    np.testing.assert_array_equal(fb.read("albedoAndDepth"), want["ad"])
+    np.testing.assert_array_equal(fb.read("depth").view(np.uint32), want["depth"])
