@@ -55,10 +55,19 @@ __global__ void __launch_bounds__(256) rm_display_kernel(const float4* __restric
             sampleCount = g_add(sampleCount, factor);
             const vec2 uv = texcoord + texOffset;
             // NEAREST + REPEAT: texel = floor(uv * size) mod size
-            long long i = (long long)floor(g_mul(uv.x, (float)W));
-            long long j = (long long)floor(g_mul(uv.y, (float)H));
-            i %= W; if (i < 0) i += W;
-            j %= H; if (j < 0) j += H;
+            const float fi = floor(g_mul(uv.x, (float)W)), fj = floor(g_mul(uv.y, (float)H));
+            long long i, j;
+            if (fabsf(fi) < 1.0e9f && fabsf(fj) < 1.0e9f) {
+                // 32-bit wrap (the 64-bit remainder is ~100 instructions); same result
+                int ii = (int)fi % W, jj = (int)fj % H;
+                if (ii < 0) ii += W;
+                if (jj < 0) jj += H;
+                i = ii; j = jj;
+            } else {
+                i = (long long)fi; j = (long long)fj;
+                i %= W; if (i < 0) i += W;
+                j %= H; if (j < 0) j += H;
+            }
             // global row j -> local row (identity when this rank owns every row)
             long long lj = j;
             if (nRanks > 1) {
