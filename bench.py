@@ -179,7 +179,7 @@ def workload_config(args) -> dict:
     return {"workload": f"guide.glsl default scene, {args.width}x{args.height}, {args.mode} mode, 1 spp/frame, "
                         f"256-pose orbit camera path (pose 0 = reference start-up view), fresh framebuffer per frame",
             "flavour": args.flavour, "pipeline": args.pipeline, "shard": args.shard if args.gpus > 1 else "none",
-            "contexts_per_gpu": 1 if (args.gpus > 1 and args.shard == "tiles") else args.contexts,
+            "contexts_per_gpu": args.contexts, "gather": args.gather if (args.gpus > 1 and args.shard == "tiles") else "none",
             "l2": "flushed before every step (160 MiB in-stream device memset, inside the timed region); "
                   "e2e alternates two framebuffer sets per context (40 B/px each) and reads every frame back",
             "steps_per_px_reference": ref_steps_per_px(args)}
@@ -208,7 +208,7 @@ def run_b200(args):
     # Frames of the path are independent, so they are dealt round-robin to `--contexts` contexts of
     # this GPU (each its own stream, module instance and ray planes): the drain phase of one frame's
     # persistent march kernel overlaps the next frame's kernels.
-    nctx = 1 if tiles else max(1, args.contexts)
+    nctx = max(1, args.contexts)
     ctxs = []
     for _ in range(nctx):
         c = rm.load_render_job_context(device=local, rank=rank if tiles else 0, n_ranks=world if tiles else 1, tile_rows=16,
@@ -240,15 +240,21 @@ def run_b200(args):
     def gather_tiles(ctx, stream, fb):
         # NCCL gather of each rank's RGBA8 rows to rank 0: equal-sized padded
         # buffers (ranks own 1..2 tiles more or less), issued in the library's stream order
-        if "send" not in gather_state:
+        g = gather_state.setdefault(id(ctx), {})
+        if "send" not in g:
             max_rows = -(-H // (16 * world)) * 16
-            gather_state["send"] = torch.zeros(max_rows * W * 4, dtype=torch.uint8, device="cuda")
-            gather_state["recv"] = [torch.empty_like(gather_state["send"]) for _ in range(world)] if rank == 0 else None
+            g["send"] = torch.zeros(max_rows * W * 4, dtype=torch.uint8, device="cuda")
+            g["recv"] = [torch.empty_like(g["send"]) for _ in range(world)] if rank == 0 else None
         n = fb.local_rows * W * 4
-        st = L.rmb_fb_copy_to_device(ctx.handle, fb.handle, 4, gather_state["send"].data_ptr(), n)
+        st = L.rmb_fb_copy_to_device(ctx.handle, fb.handle, 4, g["send"].data_ptr(), n)
         assert st == 0, ctx.last_error()
         with torch.cuda.stream(stream):
-            dist.gather(gather_state["send"], gather_state["recv"], dst=0)
+            dist.gather(g["send"], g["recv"], dst=0)
+
+    fused = None
+    if tiles and args.gather == "fused":
+        from raymarching_engine_b200.sharding import FusedTileGather
+        fused = FusedTileGather(ctxs, W, H, dist, slots=2 * nctx, blur=(args.mode == "full"))
 
     def device_step(step, flush=False):
         """one frame, everything resident in HBM (async): [L2 flush], uniforms, raymarch, display[, gather]"""
@@ -263,11 +269,24 @@ def run_b200(args):
         rm.upload_sample_uniforms(prog, s, (0.5, 1.0 / 3.0))
         st = L.rmb_render_sample(ctx.handle, prog.handle, fb.handle, 0, 0, W, H)
         assert st == 0, ctx.last_error()
-        st = L.rmb_present_device(ctx.handle, fb.handle, 1.0)
-        assert st == 0, ctx.last_error()
-        if tiles:
-            gather_tiles(ctx, stream, fb)
+        if fused and fused.blur:
+            # full mode: the display blur reads neighbour tiles, so the accumulator rows go to rank 0's
+            # full-frame planes (peer stores) and rank 0 presents the assembled frame
+            fused.scatter(ctx, fb, step)
+            fused.complete(ctx)
+            if rank == 0:
+                fused.display_assembled(ctx, step, 1.0)
+        else:
+            if fused:
+                fused.aim(ctx, step)      # the display kernel also stores into rank 0's frame `step % slots`
+            st = L.rmb_present_device(ctx.handle, fb.handle, 1.0)
+            assert st == 0, ctx.last_error()
+            if fused:
+                fused.complete(ctx)       # one-element all-reduce: every rank has presented this frame
+            elif tiles:
+                gather_tiles(ctx, stream, fb)
         ctx.fbo.delete(W, H, s.render.frameid)
+        return k
 
     def barrier():
         if dist:
@@ -326,13 +345,55 @@ def run_b200(args):
         return out
 
     checksum = 0
-    for _i, res in rm.render_frames(e2e_schemas(0, 2 * nctx + 1), ctxs):
-        assert res["success"], res["why"]
-    barrier()
-    t0 = time.perf_counter()
-    for _i, res in rm.render_frames(e2e_schemas(args.warmup, args.steps), ctxs):
-        assert res["success"], res["why"]
-        checksum += int(res["rgba8"][0, 0, 0]) + int(res["rgba8"][-1, -1, 3])   # the host reads the result
+    d2h_bytes = W * H * 8
+
+    def e2e_tiles(first, count):
+        """tile-sharded frames end to end: every rank renders + presents its rows (uniforms from the
+        host every frame), the frame is assembled on rank 0 (fused peer stores, or NCCL gather) and rank 0
+        reads it back to pinned host memory; the readback of frame k overlaps frame k+1."""
+        nonlocal checksum
+        slots = 2 * nctx
+        pinned = torch.empty((slots, H, W, 4), dtype=torch.uint8, pin_memory=True) if rank == 0 else None
+        pending = []
+        for i in range(count):
+            k = device_step(first + i)
+            if rank == 0:
+                with torch.cuda.stream(streams[k]):
+                    if fused:
+                        pinned[(first + i) % slots].copy_(fused.frame_tensor(first + i), non_blocking=True)
+                    else:
+                        flat = pinned[(first + i) % slots].view(-1)
+                        off = 0
+                        for r in range(world):
+                            n = len(sh.owned_rows(H, 16, world, r)) * W * 4
+                            flat[off:off + n].copy_(gather_state[id(ctxs[k])]["recv"][r][:n], non_blocking=True)
+                            off += n
+                ev = torch.cuda.Event()
+                ev.record(streams[k])
+                pending.append((ev, (first + i) % slots))
+                while len(pending) >= slots:
+                    e, sl = pending.pop(0)
+                    e.synchronize()
+                    checksum += int(pinned[sl, 0, 0, 0]) + int(pinned[sl, -1, -1, 3])
+        for e, sl in pending:
+            e.synchronize()
+            checksum += int(pinned[sl, 0, 0, 0]) + int(pinned[sl, -1, -1, 3])
+
+    if tiles:
+        import raymarching_engine_b200.sharding as sh
+        d2h_bytes = W * H * 4
+        e2e_tiles(0, 2 * nctx + 1)
+        barrier()
+        t0 = time.perf_counter()
+        e2e_tiles(args.warmup, args.steps)
+    else:
+        for _i, res in rm.render_frames(e2e_schemas(0, 2 * nctx + 1), ctxs):
+            assert res["success"], res["why"]
+        barrier()
+        t0 = time.perf_counter()
+        for _i, res in rm.render_frames(e2e_schemas(args.warmup, args.steps), ctxs):
+            assert res["success"], res["why"]
+            checksum += int(res["rgba8"][0, 0, 0]) + int(res["rgba8"][-1, -1, 3])   # the host reads the result
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     barrier()
@@ -391,7 +452,7 @@ def run_b200(args):
         "ms_per_step": total_ms / max(args.steps, 1), "higher_is_better": True, "scaling": "strong" if tiles else "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args),
         "roofline": roofline,
-        "e2e": {"value": e2e_value, "unit": "Mpx/s", "h2d_bytes_per_step": 712, "d2h_bytes_per_step": W * H * 8,
+        "e2e": {"value": e2e_value, "unit": "Mpx/s", "h2d_bytes_per_step": 712, "d2h_bytes_per_step": d2h_bytes,
                 "ms_per_step": 1e3 * e2e_s / max(args.steps, 1)},
         "gpu_launches": gpu_launches,   # counted by the library: every kernel it launched in the device-resident timed loop
         "clocks": clocks,
@@ -404,6 +465,8 @@ def run_b200(args):
         line["cpu_baseline"] = {"value": mpx, "unit": "Mpx/s", "cores": cores, "kind": "port", "sample": desc, "seconds": secs}
     if rank == 0:
         print(json.dumps(line), flush=True)
+    if fused:
+        fused.close()
     for c in ctxs:
         c.close()
     if dist:
@@ -421,6 +484,8 @@ def main():
     ap.add_argument("--mode", default="preview", choices=["preview", "full"])
     ap.add_argument("--flavour", default="exact", choices=["exact", "fast"])
     ap.add_argument("--shard", default="poses", choices=["poses", "tiles"])
+    ap.add_argument("--gather", default="fused", choices=["fused", "nccl"],
+                    help="--shard tiles: fused = display kernel stores into rank 0's frame over NVLink (CUDA IPC); nccl = torch.distributed.gather")
     ap.add_argument("--pipeline", default="wavefront", choices=["wavefront", "megakernel"])
     ap.add_argument("--contexts", type=int, default=2, help="contexts (streams) per GPU the independent frames are dealt to")
     ap.add_argument("--cpu-band-rows", type=int, default=360)

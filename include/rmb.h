@@ -155,6 +155,25 @@ rmb_status rmb_present_device(rmb_ctx* ctx, rmb_fb* fb, float brightness);
 rmb_status rmb_present_async(rmb_ctx* ctx, rmb_fb* fb, float brightness, uint8_t* rgba8_host, float* depth_host);
 rmb_status rmb_present_wait(rmb_ctx* ctx, rmb_fb* fb);
 
+/* ---- multi-GPU tile gather, fused into the display pass --------------------------------------
+ * (the reference has one WebGL context and no counterpart.)  With a gather target set,
+ * the display kernel of rmb_present* stores every RGBA8 pixel a second time, at its GLOBAL row, into
+ * `rgba8_full_frame` (width*height*4 bytes, row 0 = bottom).  Pointing every rank's context at ONE
+ * buffer - rank 0's, mapped into the other processes with rmb_ipc_export / rmb_ipc_open (CUDA IPC,
+ * peer access over NVLink) - assembles the frame with coalesced peer stores and no separate collective;
+ * the caller only orders "all ranks have presented" (e.g. one NCCL all-reduce of a flag per frame on
+ * the contexts' streams).  NULL switches the second store off. */
+rmb_status rmb_ctx_set_gather_target(rmb_ctx* ctx, void* rgba8_full_frame, size_t bytes);
+/* Frames whose display pass blurs (full mode with depth of field: display.frag:25-55 reads up to 16 rows
+ * either side, REPEAT-wrapped) cannot be presented tile by tile: every rank scatters its rows of the
+ * colour (which 0) and normal+dofRadius (which 1) accumulators into full-frame planes on one rank
+ * (peer memory), which then runs the display pass over the assembled planes. */
+rmb_status rmb_fb_scatter_rows(rmb_ctx* ctx, rmb_fb* fb, int which, void* dst_full_plane);
+rmb_status rmb_display_planes(rmb_ctx* ctx, const void* color_full, const void* nd_full, void* rgba8_out, int width, int height, float brightness);
+rmb_status rmb_ipc_export(void* device_ptr, unsigned char handle64[64]);
+rmb_status rmb_ipc_open(rmb_ctx* ctx, const unsigned char handle64[64], void** device_ptr);
+rmb_status rmb_ipc_close(rmb_ctx* ctx, void* device_ptr);
+
 /* ---- inspection (tests, benchmarks) --------------------------------------------------------- */
 /* which: 0 colour (float4), 1 normal+dofRadius (4 x binary16), 2 albedo+depth (4 x binary16),
  *        3 depth (float), 4 RGBA8 of the last present */
@@ -181,6 +200,9 @@ rmb_status rmb_measure_fp32_peak(rmb_ctx* ctx, double seconds, double* tflops);
 /* host-only helper: rows with global index < g owned by `rank` under the round-robin row-tile
  * deal (tile t -> rank t % n_ranks).  -1 on bad arguments.  Needs no GPU. */
 int rmb_owned_rows_below(int g, int height, int tile_rows, int n_ranks, int rank);
+/* plain device allocations (a whole cudaMalloc each, so they can be exported with rmb_ipc_export) */
+void* rmb_device_alloc(rmb_ctx* ctx, size_t bytes);
+void rmb_device_free(rmb_ctx* ctx, void* p);
 /* pinned host memory for the caller's readback buffers */
 void* rmb_host_alloc(size_t bytes);
 void rmb_host_free(void* p);

@@ -19,11 +19,11 @@ UNIFORM_F, UNIFORM_I, UNIFORM_UI = 0, 1, 2
 
 # every symbol include/rmb.h declares; tests check that the library exports all of them
 EXPORTED_SYMBOLS = [
-    "rmb_abi_version", "rmb_ctx_create", "rmb_ctx_destroy", "rmb_last_error", "rmb_ctx_stream", "rmb_sync", "rmb_ctx_set_pipeline", "rmb_ctx_launch_count", "rmb_ctx_timing",
+    "rmb_abi_version", "rmb_ctx_create", "rmb_ctx_destroy", "rmb_last_error", "rmb_ctx_stream", "rmb_sync", "rmb_ctx_set_pipeline", "rmb_ctx_launch_count", "rmb_ctx_timing", "rmb_ctx_set_gather_target", "rmb_fb_scatter_rows", "rmb_display_planes", "rmb_ipc_export", "rmb_ipc_open", "rmb_ipc_close",
     "rmb_program_get", "rmb_program_source", "rmb_program_kernel_attr", "rmb_uniform_set", "rmb_uniform_set_array",
     "rmb_uniform_matrix4", "rmb_fb_acquire", "rmb_fb_release", "rmb_fb_local_rows", "rmb_fb_global_row",
     "rmb_render_sample", "rmb_present", "rmb_present_device", "rmb_present_async", "rmb_present_wait", "rmb_fb_device_ptr", "rmb_fb_plane_bytes",
-    "rmb_fb_read", "rmb_fb_write", "rmb_fb_copy_to_device", "rmb_counters_read", "rmb_probe", "rmb_compile_only", "rmb_host_alloc",
+    "rmb_fb_read", "rmb_fb_write", "rmb_fb_copy_to_device", "rmb_counters_read", "rmb_probe", "rmb_compile_only", "rmb_host_alloc", "rmb_device_alloc", "rmb_device_free",
     "rmb_host_free", "rmb_measure_fp32_peak", "rmb_owned_rows_below",
 ]
 
@@ -54,6 +54,12 @@ def _load() -> C.CDLL:
         "rmb_ctx_set_pipeline": (i, [vp, i]),
         "rmb_ctx_launch_count": (C.c_uint64, [vp]),
         "rmb_ctx_timing": (i, [vp, i, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
+        "rmb_ctx_set_gather_target": (i, [vp, vp, sz]),
+        "rmb_fb_scatter_rows": (i, [vp, vp, i, vp]),
+        "rmb_display_planes": (i, [vp, vp, vp, vp, i, i, f]),
+        "rmb_ipc_export": (i, [vp, C.c_char_p]),
+        "rmb_ipc_open": (i, [vp, C.c_char_p, C.POINTER(vp)]),
+        "rmb_ipc_close": (i, [vp, vp]),
         "rmb_program_get": (i, [vp, cp, sz, i, C.POINTER(SpecUniform), i, C.POINTER(vp), cp, cp, sz]),
         "rmb_program_source": (cp, [vp]),
         "rmb_program_kernel_attr": (i, [vp, i, C.POINTER(i), C.POINTER(i)]),
@@ -80,6 +86,8 @@ def _load() -> C.CDLL:
         "rmb_measure_fp32_peak": (i, [vp, C.c_double, C.POINTER(C.c_double)]),
         "rmb_owned_rows_below": (i, [i, i, i, i, i]),
         "rmb_host_alloc": (vp, [sz]),
+        "rmb_device_alloc": (vp, [vp, sz]),
+        "rmb_device_free": (None, [vp, vp]),
         "rmb_host_free": (None, [vp]),
     }
     for name, (res, args) in proto.items():

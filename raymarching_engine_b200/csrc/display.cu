@@ -30,7 +30,7 @@ __device__ __forceinline__ float h2f(unsigned short h) {
 }
 
 __global__ void __launch_bounds__(256) rm_display_kernel(const float4* __restrict__ color, const ushort4* __restrict__ nd,
-                                                         uchar4* __restrict__ out, int W, int localRows, int H,
+                                                         uchar4* __restrict__ out, uchar4* __restrict__ gather, int W, int localRows, int H,
                                                          int tileRows, int nRanks, int rank, float brightness) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int ly = blockIdx.y;
@@ -89,10 +89,35 @@ __global__ void __launch_bounds__(256) rm_display_kernel(const float4* __restric
         b[cpt] = (unsigned char)(int)floor(g_add(g_mul(v, 255.0f), 0.5f));
     }
     out[idx] = make_uchar4(b[0], b[1], b[2], b[3]);
+    // fused tile gather (multi-GPU row-tile sharding): the same pixel goes straight into the assembled
+    // full frame - usually rank 0's memory mapped over NVLink (CUDA IPC) - at its GLOBAL row.  A warp
+    // writes one 128-byte line, so the peer stores are fully coalesced; no separate collective moves pixels.
+    if (gather) gather[(size_t)gy * (size_t)W + (size_t)x] = make_uchar4(b[0], b[1], b[2], b[3]);
 }
 
 }  // namespace disp
 }  // namespace xg
+
+// Row scatter for multi-GPU frames that need the display blur (full mode with depth of field): a rank
+// copies its local rows of an accumulator plane into a FULL-FRAME plane (usually rank 0's memory over
+// NVLink) at their global rows; rank 0 then runs the display pass over the assembled planes
+// (SURVEY.md 8e caveat: the blur reads +-16 neighbour rows with REPEAT wrap).  16-byte chunks.
+__global__ void __launch_bounds__(256) rm_scatter_rows_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int rowVec,
+                                                              int localRows, int tileRows, int nRanks, int rank) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    const int ly = blockIdx.y;
+    if (v >= rowVec || ly >= localRows) return;
+    const int t = ly / tileRows;
+    const int gy = (t * nRanks + rank) * tileRows + (ly - t * tileRows);
+    dst[(size_t)gy * (size_t)rowVec + (size_t)v] = src[(size_t)ly * (size_t)rowVec + (size_t)v];
+}
+extern "C" cudaError_t rmb_launch_scatter_rows(const void* src, void* dst, int row_bytes, int local_rows, int tile_rows, int n_ranks,
+                                               int rank, cudaStream_t stream) {
+    const int rowVec = row_bytes / 16;
+    dim3 block(256, 1, 1), grid((unsigned)((rowVec + 255) / 256), (unsigned)local_rows, 1);
+    rm_scatter_rows_kernel<<<grid, block, 0, stream>>>((const uint4*)src, (uint4*)dst, rowVec, local_rows, tile_rows, n_ranks, rank);
+    return cudaGetLastError();
+}
 
 // FP32 FMA throughput probe: the roofline denominator for this FP32-bound path is not in
 // MEASURED_PEAKS.json (which has HBM and bf16 only), so bench.py measures it live.  Each thread
@@ -116,10 +141,10 @@ extern "C" cudaError_t rmb_launch_fp32_peak(float* scratch, int blocks, int iter
     return cudaGetLastError();
 }
 
-extern "C" cudaError_t rmb_launch_display(const void* color, const void* nd, void* rgba8, int W, int local_rows, int H,
+extern "C" cudaError_t rmb_launch_display(const void* color, const void* nd, void* rgba8, void* gather, int W, int local_rows, int H,
                                           int tile_rows, int n_ranks, int rank, float brightness, cudaStream_t stream) {
     dim3 block(256, 1, 1), grid((unsigned)((W + 255) / 256), (unsigned)local_rows, 1);
-    xg::disp::rm_display_kernel<<<grid, block, 0, stream>>>((const float4*)color, (const ushort4*)nd, (uchar4*)rgba8, W,
+    xg::disp::rm_display_kernel<<<grid, block, 0, stream>>>((const float4*)color, (const ushort4*)nd, (uchar4*)rgba8, (uchar4*)gather, W,
                                                             local_rows, H, tile_rows, n_ranks, rank, brightness);
     return cudaGetLastError();
 }
