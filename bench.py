@@ -45,12 +45,18 @@ N_POSES = 256
 FLUSH_BYTES = 160 << 20   # > the 126 MB L2 of a B200
 
 
-def orbit_pose(k: int):
-    """Pose k of the synthetic camera path: radius 10 around bigSphereCenter = (0,0,10) in the XZ
-    plane, looking at the centre.  rotation = gl-matrix mat4.fromYRotation(-theta), column-major."""
+# orbit centre and radius of the synthetic camera path per scene (default: the guide scene's
+# bigSphereCenter = (0,0,10), radius 10, so that pose 0 is the reference's start-up view at the origin)
+SCENE_ORBITS = {"mandelbulb": ((0.0, 0.0, 0.0), 3.0)}
+
+
+def orbit_pose(k: int, scene: str = "guide"):
+    """Pose k of the synthetic camera path: a circle in the XZ plane around the scene's centre, looking
+    at the centre.  rotation = gl-matrix mat4.fromYRotation(-theta), column-major."""
+    (cx, cy, cz), radius = SCENE_ORBITS.get(scene, ((0.0, 0.0, 10.0), 10.0))
     theta = 2.0 * math.pi * (k % N_POSES) / N_POSES
     c, s = math.cos(theta), math.sin(theta)
-    position = (10.0 * s, 0.0, 10.0 - 10.0 * c)
+    position = (cx + radius * s, cy, cz - radius * c)
     phi = -theta
     cp, sp = math.cos(phi), math.sin(phi)
     rotation = (cp, 0.0, -sp, 0.0, 0.0, 1.0, 0.0, 0.0, sp, 0.0, cp, 0.0, 0.0, 0.0, 0.0, 1.0)
@@ -58,11 +64,15 @@ def orbit_pose(k: int):
     return position, rotation
 
 
-def make_schema(rm, src, custom, W, H, mode, pose, frameid):
-    s = rm.default_schema(src, custom, width=W, height=H, renderMode=mode, frameid=frameid)
-    s.camera.position, s.camera.rotation = orbit_pose(pose)
+def make_schema(rm, src, custom, W, H, mode, pose, frameid, scene="guide", step_counts=None, spp=1):
+    s = rm.default_schema(src, custom, width=W, height=H, renderMode=mode, frameid=frameid, samplesPerPixel=spp)
+    s.camera.position, s.camera.rotation = orbit_pose(pose, scene)
+    if step_counts:
+        s.reflectionIterationCounts = list(step_counts)
     if mode == "full":
         s.lights = [rm.default_light()]
+        if scene in SCENE_ORBITS:       # the default light sits at the origin: move it outside this scene's object
+            s.lights[0].position = (2.0, 3.0, -4.0)
     return s
 
 
@@ -112,7 +122,7 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_reference_sample(W, H, mode, band_rows, nthreads=None):
+def cpu_reference_sample(W, H, mode, band_rows, nthreads=None, scene="guide", counts=None):
     """Times the CPU restatement of the reference shader (oracle/) on a band of `band_rows` rows of
     one W x H frame (every pixel costs the same in the reference: no early exit), plus the display
     pass scaled to the band.  Returns (Mpx/s, seconds, cores, description)."""
@@ -120,9 +130,12 @@ def cpu_reference_sample(W, H, mode, band_rows, nthreads=None):
     import pyoracle
     import raymarching_engine_b200.params as params
     import raymarching_engine_b200.schema as schema_mod
-    src = (ROOT / "scenes" / "guide.glsl").read_text()
+    src = (ROOT / "scenes" / f"{scene}.glsl").read_text()
     custom = params.default_custom_settings(src)
     s = schema_mod.default_schema(src, custom, width=W, height=H, renderMode=mode)
+    s.camera.position, s.camera.rotation = orbit_pose(0, scene)
+    if counts:
+        s.reflectionIterationCounts = list(counts)
     if mode == "full":
         s.lights = [schema_mod.default_light()]
     cores = nthreads or os.cpu_count() or 1
@@ -130,13 +143,23 @@ def cpu_reference_sample(W, H, mode, band_rows, nthreads=None):
     U = pyoracle.uniforms_from_schema(s, (0.5, 1.0 / 3.0))
     y0 = max(0, (H - band_rows) // 2)
     t0 = time.perf_counter()
-    pyoracle.render_sample("guide", custom, U, acc, (0, y0, W, band_rows), cores)
+    pyoracle.render_sample(scene, custom, U, acc, (0, y0, W, band_rows), cores)
     t1 = time.perf_counter()
     pyoracle.display(acc, 1.0, cores)
     t2 = time.perf_counter()
     px = W * min(band_rows, H)
     secs = (t1 - t0) + (t2 - t1) * (px / (W * H))
     return px / secs / 1e6, secs, cores, f"{W}x{min(band_rows, H)} band of one {W}x{H} {mode}-mode frame, raymarch + display, {cores} threads"
+
+
+def _json_safe(x):
+    if isinstance(x, float) and (math.isnan(x) or math.isinf(x)):
+        return None
+    if isinstance(x, dict):
+        return {k: _json_safe(v) for k, v in x.items()}
+    if isinstance(x, (list, tuple)):
+        return [_json_safe(v) for v in x]
+    return x
 
 
 def run_reference(args):
@@ -150,7 +173,7 @@ def run_reference(args):
     band = args.ref_band_rows
     vals = []
     for i in range(args.warmup + args.steps):
-        mpx, secs, cores, desc = cpu_reference_sample(W, H, args.mode, band)
+        mpx, secs, cores, desc = cpu_reference_sample(W, H, args.mode, band, None, args.scene, step_counts_of(args) if args.step_counts else None)
         if i >= args.warmup:
             vals.append((mpx, secs))
     total_s = sum(s for _, s in vals)
@@ -164,19 +187,28 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "Mpx/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "extra": {"msteps_per_s_ref_equiv": value * ref_steps_per_px(args)},
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(_json_safe(line)), flush=True)
+
+
+def step_counts_of(args):
+    return [float(x) for x in args.step_counts.split(",")] if args.step_counts else [128.0, 128.0, 64.0, 32.0, 32.0]   # index.tsx:321
 
 
 def ref_steps_per_px(args) -> float:
-    return 128.0 if args.mode == "preview" else 384.0 * 2 + 25.0
+    """SDF evaluations per pixel-sample the reference executes (SURVEY.md section 3.3): preview steps[0];
+    full sum(steps) * (1 + lights) + 5 per bounce (4 normal probes + the subsurface probe), 1 light."""
+    c = step_counts_of(args)
+    return c[0] if args.mode == "preview" else sum(c) * 2 + 5.0 * len(c)
 
 
 def metric_name(args) -> str:
-    return f"megapixels/s, default scene (guide.glsl) {args.width}x{args.height}, {args.mode} mode"
+    what = "default scene (guide.glsl)" if args.scene == "guide" else f"{args.scene}.glsl"
+    return f"megapixels/s, {what} {args.width}x{args.height}, {args.mode} mode" + (f", {args.spp} spp" if args.spp > 1 else "")
 
 
 def workload_config(args) -> dict:
-    return {"workload": f"guide.glsl default scene, {args.width}x{args.height}, {args.mode} mode, 1 spp/frame, "
+    what = "guide.glsl default scene" if args.scene == "guide" else f"{args.scene}.glsl"
+    return {"workload": f"{what}, {args.width}x{args.height}, {args.mode} mode, {args.spp} spp/frame, steps {step_counts_of(args)}, "
                         f"256-pose orbit camera path (pose 0 = reference start-up view), fresh framebuffer per frame",
             "flavour": args.flavour, "pipeline": args.pipeline, "shard": args.shard if args.gpus > 1 else "none",
             "contexts_per_gpu": args.contexts, "gather": args.gather if (args.gpus > 1 and args.shard == "tiles") else "none",
@@ -216,8 +248,11 @@ def run_b200(args):
         if c is None:
             raise SystemExit("bench.py: " + rm.context_error())
         ctxs.append(c)
-    src = (ROOT / "scenes" / "guide.glsl").read_text()
+    src = (ROOT / "scenes" / f"{args.scene}.glsl").read_text()
     custom = rm.default_custom_settings(src)
+    counts = step_counts_of(args) if args.step_counts else None
+    halton2, halton3 = rm.halton(2), rm.halton(3)
+    sample_noise = [(next(halton2), next(halton3)) for _ in range(args.spp)]   # every frame restarts the sequence
     streams = [torch.cuda.ExternalStream(c.stream(), device=dev) for c in ctxs]
     flush_bufs = [torch.empty(FLUSH_BYTES, dtype=torch.uint8, device="cuda") for _ in ctxs]
     L = rm._lib.lib
@@ -264,11 +299,12 @@ def run_b200(args):
             with torch.cuda.stream(stream):
                 flush_bufs[k].zero_()
         frame_counter[0] += 1
-        s = make_schema(rm, src, custom, W, H, args.mode, pose_of(step), frame_counter[0])
+        s = make_schema(rm, src, custom, W, H, args.mode, pose_of(step), frame_counter[0], args.scene, counts, args.spp)
         fb = ctx.fbo.create(W, H, s.render.frameid)
-        rm.upload_sample_uniforms(prog, s, (0.5, 1.0 / 3.0))
-        st = L.rmb_render_sample(ctx.handle, prog.handle, fb.handle, 0, 0, W, H)
-        assert st == 0, ctx.last_error()
+        for noise in sample_noise:
+            rm.upload_sample_uniforms(prog, s, noise)
+            st = L.rmb_render_sample(ctx.handle, prog.handle, fb.handle, 0, 0, W, H)
+            assert st == 0, ctx.last_error()
         if fused and fused.blur:
             # full mode: the display blur reads neighbour tiles, so the accumulator rows go to rank 0's
             # full-frame planes (peer stores) and rank 0 presents the assembled frame
@@ -332,7 +368,7 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms = float(t.item())
     frames = args.steps * (1 if tiles else world)
-    value = frames * W * H / (total_ms * 1e-3) / 1e6
+    value = frames * W * H * args.spp / (total_ms * 1e-3) / 1e6     # pixel-samples per second
 
     # ---- timed: end to end through the public API (rm.render_frames = do_render_job per frame with a
     # pipelined presenter): uniforms from host memory every frame, RGBA8 + fp32 depth of every frame
@@ -341,7 +377,7 @@ def run_b200(args):
         out = []
         for i in range(count):
             frame_counter[0] += 1
-            out.append(make_schema(rm, src, custom, W, H, args.mode, pose_of(first + i), frame_counter[0]))
+            out.append(make_schema(rm, src, custom, W, H, args.mode, pose_of(first + i), frame_counter[0], args.scene, counts, args.spp))
         return out
 
     checksum = 0
@@ -401,7 +437,7 @@ def run_b200(args):
         t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
-    e2e_value = frames * W * H / e2e_s / 1e6
+    e2e_value = frames * W * H * args.spp / e2e_s / 1e6
     clocks = sampler.stop()
 
     # ---- roofline of the hot kernel (the persistent march kernel), timed ALONE: with several
@@ -423,6 +459,8 @@ def run_b200(args):
     sm_max = clocks.get("sm_max_mhz") or 1965.0
     nominal_peak = sm_count * 128 * 2 * sm_max * 1e6 / 1e12
     flop_per_step = FLOP_PER_PREVIEW_STEP if args.mode == "preview" else FLOP_PER_CASTRAY_STEP
+    if args.scene != "guide":
+        flop_per_step = float("nan")    # the algorithmic flop count is defined for the default scene only
     kernel_s = hot_ms * 1e-3
     achieved = evals_solo * flop_per_step / kernel_s / 1e12 if kernel_s > 0 else 0.0
     if wavefront:
@@ -461,10 +499,10 @@ def run_b200(args):
     }
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        mpx, secs, cores, desc = cpu_reference_sample(W, H, args.mode, args.cpu_band_rows)
+        mpx, secs, cores, desc = cpu_reference_sample(W, H, args.mode, args.cpu_band_rows, None, args.scene, counts)
         line["cpu_baseline"] = {"value": mpx, "unit": "Mpx/s", "cores": cores, "kind": "port", "sample": desc, "seconds": secs}
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        print(json.dumps(_json_safe(line)), flush=True)
     if fused:
         fused.close()
     for c in ctxs:
@@ -482,6 +520,9 @@ def main():
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--mode", default="preview", choices=["preview", "full"])
+    ap.add_argument("--scene", default="guide", help="scenes/<name>.glsl (BASELINE.json config 4: mandelbulb)")
+    ap.add_argument("--step-counts", default="", help="comma-separated reflectionIterationCounts (config 4: 512)")
+    ap.add_argument("--spp", type=int, default=1, help="samples per pixel per frame (config 5: 16)")
     ap.add_argument("--flavour", default="exact", choices=["exact", "fast"])
     ap.add_argument("--shard", default="poses", choices=["poses", "tiles"])
     ap.add_argument("--gather", default="fused", choices=["fused", "nccl"],
