@@ -41,6 +41,11 @@ typedef enum rmb_status {
 /* rmb_program_get flavours */
 #define RMB_FLAVOUR_EXACT 0 /* scene arithmetic = unfused IEEE fp32, bit-identical to the CPU oracle */
 #define RMB_FLAVOUR_FAST 1  /* scene arithmetic may use FMA contraction and approximate intrinsics   */
+/* Measurement aid, not a product mode: the exact flavour with ONE implementation-defined GLSL choice
+ * flipped - mod(x,y) = x - y*floor(x/y) with a true division and no fused multiply-add, as the GLSL ES
+ * 3.00 text writes it - i.e. a second conforming implementation of the reference shader.  Comparing it
+ * with RMB_FLAVOUR_EXACT shows how far two legal implementations drift apart on the same inputs. */
+#define RMB_FLAVOUR_EXACT_ALT 2
 
 /* uniform base types, renderer/Uniforms.tsx:7-9 ("f" | "i" | "ui") */
 #define RMB_UNIFORM_F 0

@@ -7,7 +7,7 @@ get_custom_shader_params.  All rendering goes through libraymarch_b200.so (inclu
 import fails if the library has not been built and there is no CPU fallback.
 """
 from . import _lib  # noqa: F401  (raises ImportError when the CUDA library is missing)
-from ._lib import FLAVOUR_EXACT, FLAVOUR_FAST
+from ._lib import FLAVOUR_EXACT, FLAVOUR_EXACT_ALT, FLAVOUR_FAST
 from .executor import (FramebufferInfo, Program, RenderJobContext, ShaderError, builtin_uniforms, context_error,
                        do_render_job, load_render_job_context, make_presenter, render_frames, reset_halton, run_job,
                        upload_sample_uniforms)

@@ -14,7 +14,7 @@ _HERE = Path(__file__).resolve().parent
 LIB_PATH = _HERE / "libraymarch_b200.so"
 
 RMB_OK, RMB_ERR_FRAGMENT, RMB_ERR_PROGRAM, RMB_ERR_GENERAL, RMB_ERR_INVALID = range(5)
-FLAVOUR_EXACT, FLAVOUR_FAST = 0, 1
+FLAVOUR_EXACT, FLAVOUR_FAST, FLAVOUR_EXACT_ALT = 0, 1, 2
 UNIFORM_F, UNIFORM_I, UNIFORM_UI = 0, 1, 2
 
 # every symbol include/rmb.h declares; tests check that the library exports all of them

@@ -167,7 +167,12 @@ RM_HD float round(float x) {
     return t;
 }
 RM_HD float fract(float x) { return g_sub(x, g_floor(x)); }
+#if !GLSL_FAST && defined(RM_PIN_ALT) && RM_PIN_ALT
+// second conforming implementation (RMB_FLAVOUR_EXACT_ALT, measurement aid): GLSL ES 3.00 8.3 as written
+RM_HD float mod(float x, float y) { return g_sub(x, g_mul(y, g_floor(g_div(x, y)))); }
+#else
 RM_HD float mod(float x, float y) { return g_fma(-y, g_floor(g_mul(x, g_rcp(y))), x); }
+#endif
 // Domain repetition idiom `mod(x + h1, s) - h2` (and `mod(x, s) - h2`): the lowering
 // (lower_glsl.cpp) hands the four operands to rm_rep / rm_rep0.  Exact policy: the expression as
 // written.  Fast policy: when h2 == s/2 (a centred cell, the canonical opRep form) it is the centred

@@ -28,7 +28,8 @@ def main():
     import bench
     src = (ROOT / "scenes" / "guide.glsl").read_text()
     custom = rm.default_custom_settings(src)
-    ctxs = {"exact": rm.load_render_job_context(device=0, flavour=rm.FLAVOUR_EXACT), "fast": rm.load_render_job_context(device=0, flavour=rm.FLAVOUR_FAST)}
+    ctxs = {"exact": rm.load_render_job_context(device=0, flavour=rm.FLAVOUR_EXACT), "fast": rm.load_render_job_context(device=0, flavour=rm.FLAVOUR_FAST),
+            "alt": rm.load_render_job_context(device=0, flavour=rm.FLAVOUR_EXACT_ALT)}
     report = {"width": args.width, "height": args.height, "cases": []}
     fid = 1
     for mode in args.modes:
@@ -51,6 +52,14 @@ def main():
             case["hit_fraction"] = float(hit.mean())
             case["fast_vs_exact_hit_depth_within_1e-4"] = float((rel[hit] <= 1e-4).mean()) if hit.any() else 1.0
             case["fast_vs_exact_depth_within_1e-4_all_px"] = float((rel <= 1e-4).mean())
+            # how far a second CONFORMING implementation of the reference (mod() with a true division, no
+            # fused multiply-add) drifts from the pinned one: the reference's own implementation-defined noise
+            c2 = got["alt"]
+            d3 = np.abs(a[0].astype(np.int32) - c2[0].astype(np.int32)).max(axis=2)
+            case["alt_conforming_vs_exact_rgba8_within_1"] = float((d3 <= 1).mean())
+            case["alt_conforming_vs_exact_rgba8_identical"] = float((d3 == 0).mean())
+            rel3 = np.abs(a[1] - c2[1]) / np.maximum(np.abs(a[1]), 1e-30)
+            case["alt_conforming_vs_exact_hit_depth_within_1e-4"] = float((rel3[hit] <= 1e-4).mean()) if hit.any() else 1.0
             if args.oracle:
                 import pyoracle
                 s = bench.make_schema(rm, src, custom, args.width, args.height, mode, pose, 1)

@@ -4,7 +4,7 @@ TAG=${1:-cfg}
 O=gpurun_out
 mkdir -p $O
 run() { name=$1; shift
-  python bench.py --no-cpu-baseline "$@" > $O/cfg_${TAG}_${name}.json 2> $O/cfg_${TAG}_${name}.err
+  python bench.py --no-cpu-baseline --no-second-flavour "$@" > $O/cfg_${TAG}_${name}.json 2> $O/cfg_${TAG}_${name}.err
   python - <<PY
 import json
 try:

@@ -17,5 +17,5 @@ except Exception as e:
     print("N=$N $1 $2 FAILED", e); print(open("$O/bench_${TAG}_n${N}_$1_$2.err").read()[-3000:])
 PY
 done
-python bench.py --steps 20 --warmup 5 --width 3840 --height 2160 --no-cpu-baseline > $O/bench_${TAG}_n1_4k.json 2>$O/bench_${TAG}_n1_4k.err; python -c "
+python bench.py --steps 20 --warmup 5 --width 3840 --height 2160 --no-cpu-baseline --no-second-flavour > $O/bench_${TAG}_n1_4k.json 2>$O/bench_${TAG}_n1_4k.err; python -c "
 import json; d=json.load(open('$O/bench_${TAG}_n1_4k.json')); print('N=1 4K', round(d['value'],1), 'e2e', round(d['e2e']['value'],1), 'frac', round(d['roofline']['frac'],4))"

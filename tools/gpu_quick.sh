@@ -7,7 +7,7 @@ if [ -z "$NOTEST" ]; then python -m pytest tests -m gpu -x -q > $O/pytest_${TAG}
 for nc in ${CTXS:-1 2}; do
 for cfg in "preview exact" "preview fast" "full exact" "full fast"; do
   set -- $cfg
-  python bench.py --steps 24 --warmup 6 --mode $1 --flavour $2 --contexts $nc --no-cpu-baseline > $O/bench_${TAG}_$1_$2_c$nc.json 2> $O/bench_${TAG}_$1_$2_c$nc.err
+  python bench.py --steps 24 --warmup 6 --mode $1 --flavour $2 --contexts $nc --no-cpu-baseline --no-second-flavour > $O/bench_${TAG}_$1_$2_c$nc.json 2> $O/bench_${TAG}_$1_$2_c$nc.err
   python - <<PY
 import json
 try:

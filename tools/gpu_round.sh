@@ -8,7 +8,7 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv > $O/env_${TAG}
 python -m pytest tests -m gpu -x -q > $O/pytest_${TAG}.log 2>&1; tail -5 $O/pytest_${TAG}.log
 for cfg in "preview exact" "preview fast" "full exact" "full fast"; do
   set -- $cfg
-  python bench.py --steps 20 --warmup 5 --mode $1 --flavour $2 --no-cpu-baseline > $O/bench_${TAG}_$1_$2.json 2> $O/bench_${TAG}_$1_$2.err
+  python bench.py --steps 20 --warmup 5 --mode $1 --flavour $2 --no-cpu-baseline --no-second-flavour > $O/bench_${TAG}_$1_$2.json 2> $O/bench_${TAG}_$1_$2.err
   python - <<PY
 import json
 try:
@@ -20,11 +20,11 @@ PY
 done
 python tools/flavour_report.py --poses 0 40 --modes preview full > $O/flavour_${TAG}.json 2> $O/flavour_${TAG}.err; cat $O/flavour_${TAG}.json | tr -d '\n ' ; echo
 if [ "$QUICK" != "quick" ]; then
-ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-file $O/launches_${TAG}.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline > $O/ncu_launches_${TAG}.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-file $O/launches_${TAG}.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-second-flavour > $O/ncu_launches_${TAG}.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:rm_wf_march -s 3 -c 1 -o $O/prof_preview_fast_${TAG} \
-    python bench.py --steps 2 --warmup 3 --flavour fast --no-cpu-baseline > $O/ncu_${TAG}.log 2>&1
+    python bench.py --steps 2 --warmup 3 --flavour fast --no-cpu-baseline --no-second-flavour > $O/ncu_${TAG}.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:rm_wf_march -s 12 -c 1 -o $O/prof_full_fast_${TAG} \
-    python bench.py --steps 2 --warmup 3 --mode full --flavour fast --no-cpu-baseline >> $O/ncu_${TAG}.log 2>&1
+    python bench.py --steps 2 --warmup 3 --mode full --flavour fast --no-cpu-baseline --no-second-flavour >> $O/ncu_${TAG}.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:rm_wf_march -s 12 -c 1 -o $O/prof_full_exact_${TAG} \
-    python bench.py --steps 2 --warmup 3 --mode full --no-cpu-baseline >> $O/ncu_${TAG}.log 2>&1
+    python bench.py --steps 2 --warmup 3 --mode full --no-cpu-baseline --no-second-flavour >> $O/ncu_${TAG}.log 2>&1
 fi
