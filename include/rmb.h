@@ -1,7 +1,7 @@
 /* rmb.h -- C ABI of libraymarch_b200.so, the B200-native replacement for the WebGL2 layer under
  * radian628/raymarching-engine's render-job API.
  *
- * The reference's TypeScript host (client/src/renderer/*.tsx) talks to the GPU only through a
+ * The reference's TypeScript host (the .tsx files of client/src/renderer) talks to the GPU only through a
  * WebGL2RenderingContext.  Each entry point below replaces one group of those calls; the
  * reference interface it stands in for is cited as file:line under /root/reference/client/src.
  * An N-API addon maps these 1:1 into JavaScript; the tests drive the same

@@ -136,12 +136,27 @@ static napi_value Present(napi_env env, napi_callback_info info) {
                                    (uint8_t*)typed(env, argv[3]), t == napi_object ? (float*)typed(env, argv[4]) : NULL));
 }
 
+/* presentAsync(ctx, fb, brightness, Uint8Array rgba8, Float32Array depth | null) / presentWait(ctx, fb): the
+ * non-blocking pair (WebGL draws return immediately; only the capture waits, index.tsx:470-476) */
+static napi_value PresentAsync(napi_env env, napi_callback_info info) {
+    ARGS(5);
+    napi_valuetype t; napi_typeof(env, argv[4], &t);
+    return mk_i32(env, rmb_present_async((rmb_ctx*)ext(env, argv[0]), (rmb_fb*)ext(env, argv[1]), (float)f64(env, argv[2]),
+                                         (uint8_t*)typed(env, argv[3]), t == napi_object ? (float*)typed(env, argv[4]) : NULL));
+}
+static napi_value PresentWait(napi_env env, napi_callback_info info) {
+    ARGS(2);
+    return mk_i32(env, rmb_present_wait((rmb_ctx*)ext(env, argv[0]), (rmb_fb*)ext(env, argv[1])));
+}
+static napi_value Sync(napi_env env, napi_callback_info info) { ARGS(1); return mk_i32(env, rmb_sync((rmb_ctx*)ext(env, argv[0]))); }
+
 #define EXPORT(name, fn) do { napi_value f; napi_create_function(env, name, NAPI_AUTO_LENGTH, fn, NULL, &f); napi_set_named_property(env, exports, name, f); } while (0)
 static napi_value Init(napi_env env, napi_value exports) {
     EXPORT("ctxCreate", CtxCreate); EXPORT("ctxDestroy", CtxDestroy); EXPORT("lastError", LastError);
     EXPORT("programGet", ProgramGet); EXPORT("uniformSet", UniformSet); EXPORT("uniformSetArray", UniformSetArray);
     EXPORT("uniformMatrix4", UniformMatrix4); EXPORT("fbAcquire", FbAcquire); EXPORT("fbRelease", FbRelease);
     EXPORT("fbLocalRows", FbLocalRows); EXPORT("renderSample", RenderSample); EXPORT("present", Present);
+    EXPORT("presentAsync", PresentAsync); EXPORT("presentWait", PresentWait); EXPORT("sync", Sync);
     return exports;
 }
 NAPI_MODULE(NODE_GYP_MODULE_NAME, Init)
