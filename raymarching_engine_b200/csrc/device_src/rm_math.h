@@ -67,146 +67,215 @@ RM_HD float f_nan() { return i2f(0x7fffffff); }
 RM_HD float f_inf() { return i2f(0x7f800000); }
 
 // ---------------------------------------------------------------- trigonometric kernels
+// Two sources for the same binary64 coefficients:
+//   TrigLit  literals.  The compiler sees the values, so sin/cos/tan of compile-time constants (baked
+//            uniforms in scene code) fold away; in generated code every 64-bit literal costs two UMOVs.
+//   TrigTab  a table - on the device a (non-const) __constant__ array, which DFMA reads as
+//            constant-bank operands (one LDCU.128 fetches two).  Used by the pipeline's RNG, where the
+//            argument is never a constant and the literals were ~30 % of tan()'s instructions.
+// Identical values, identical operations: results are bit-identical whichever source is used.
+#define RM_TRIG_COEFFS                                                                                   \
+    6.36619772367581382433e-01,  /*  0 2/pi */                                                           \
+    1.57079632673412561417e+00,  /*  1 first 33 bits of pi/2 */                                          \
+    6.07710050630396597660e-11,  /*  2 next 33 bits */                                                   \
+    2.02226624879595063154e-21,  /*  3 remainder */                                                      \
+    -1.66666666666666324348e-01, 8.33333333332248946124e-03, -1.98412698298579493134e-04, /* 4 S1..S6 */ \
+    2.75573137070700676789e-06, -2.50507602534068634195e-08, 1.58969099521155010221e-10,                 \
+    4.16666666666666019037e-02, -1.38888888888741095749e-03, 2.48015872894767294178e-05, /* 10 C1..C6 */ \
+    -2.75573143513906633035e-07, 2.08757232129817482790e-09, -1.13596475577881948265e-11,                \
+    6755399441055744.0,          /* 16 2^52 + 2^51 */                                                    \
+    2147483648.0                 /* 17 2^31 */
+#if RM_DEVICE_CODE
+__device__ __constant__ double rm_trig_tab[18] = {RM_TRIG_COEFFS};
+#else
+static const double rm_trig_tab[18] = {RM_TRIG_COEFFS};
+#endif
+struct TrigTab { static RM_HD double at(int i) { return rm_trig_tab[i]; } };
+struct TrigLit {
+    static RM_HD double at(int i) {
+        const double v[18] = {RM_TRIG_COEFFS};
+        return v[i];
+    }
+};
+
 // Reduction x = k*(pi/2) + r, |r| <= pi/4, three-term Cody-Waite with fma (constants are the
 // classic split of pi/2 into 33-bit pieces).  k is returned modulo 4 in *quadrant.
+template <class K>
 RM_HD double trig_reduce(double x, int* quadrant) {
-    const double TWO_OVER_PI = 6.36619772367581382433e-01;
-    const double PIO2_1 = 1.57079632673412561417e+00;   // first 33 bits of pi/2
-    const double PIO2_2 = 6.07710050630396597660e-11;   // next 33 bits
-    const double PIO2_2T = 2.02226624879595063154e-21;  // remainder
-    const double xs = x * TWO_OVER_PI;
+    const double xs = x * K::at(0);
     double k;
-    if (dabs(xs) < 2147483648.0) {
+    if (dabs(xs) < K::at(17)) {
         // round-to-nearest-even by the 2^52+2^51 trick; the integer (two's complement) is then
         // sitting in the low mantissa bits of t, so k mod 4 is a mask - no floor / conversion
-        const double M = 6755399441055744.0;
-        const double t = xs + M;
-        k = t - M;
+        const double t = xs + K::at(16);
+        k = t - K::at(16);
         *quadrant = (int)(d2ll(t) & 3);
     } else {
         k = drint(xs);
         *quadrant = (int)dfma(-4.0, dfloor(k * 0.25), k);   // exact: k mod 4 in {0,1,2,3}
     }
-    double r = dfma(-k, PIO2_1, x);
-    r = dfma(-k, PIO2_2, r);
-    r = dfma(-k, PIO2_2T, r);
+    double r = dfma(-k, K::at(1), x);
+    r = dfma(-k, K::at(2), r);
+    r = dfma(-k, K::at(3), r);
     return r;
 }
 
 // sin(r), |r| <= pi/4  (odd minimax polynomial, degree 13)
+template <class K>
 RM_HD double ksin(double r) {
-    const double S1 = -1.66666666666666324348e-01, S2 = 8.33333333332248946124e-03,
-                 S3 = -1.98412698298579493134e-04, S4 = 2.75573137070700676789e-06,
-                 S5 = -2.50507602534068634195e-08, S6 = 1.58969099521155010221e-10;
     double z = r * r;
-    double p = dfma(z, S6, S5);
-    p = dfma(z, p, S4);
-    p = dfma(z, p, S3);
-    p = dfma(z, p, S2);
-    p = dfma(z, p, S1);
+    double p = dfma(z, K::at(9), K::at(8));
+    p = dfma(z, p, K::at(7));
+    p = dfma(z, p, K::at(6));
+    p = dfma(z, p, K::at(5));
+    p = dfma(z, p, K::at(4));
     return dfma(r * z, p, r);
 }
 
 // cos(r), |r| <= pi/4  (even minimax polynomial, degree 14)
+template <class K>
 RM_HD double kcos(double r) {
-    const double C1 = 4.16666666666666019037e-02, C2 = -1.38888888888741095749e-03,
-                 C3 = 2.48015872894767294178e-05, C4 = -2.75573143513906633035e-07,
-                 C5 = 2.08757232129817482790e-09, C6 = -1.13596475577881948265e-11;
     double z = r * r;
-    double p = dfma(z, C6, C5);
-    p = dfma(z, p, C4);
-    p = dfma(z, p, C3);
-    p = dfma(z, p, C2);
-    p = dfma(z, p, C1);
+    double p = dfma(z, K::at(15), K::at(14));
+    p = dfma(z, p, K::at(13));
+    p = dfma(z, p, K::at(12));
+    p = dfma(z, p, K::at(11));
+    p = dfma(z, p, K::at(10));
     return dfma(z * z, p, dfma(z, -0.5, 1.0));
 }
 
-RM_HD float sin_f(float x) {
+template <class K>
+RM_HD float sin_k(float x) {
     if (f_isnan(x) || f_isinf(x)) return f_nan();
     int q;
-    double r = trig_reduce((double)x, &q);
-    double s = (q & 1) ? kcos(r) : ksin(r);
+    double r = trig_reduce<K>((double)x, &q);
+    double s = (q & 1) ? kcos<K>(r) : ksin<K>(r);
     if (q & 2) s = -s;
     if (x == 0.0f) return x;  // keep signed zero
     return (float)s;
 }
 
-RM_HD float cos_f(float x) {
+template <class K>
+RM_HD float cos_k(float x) {
     if (f_isnan(x) || f_isinf(x)) return f_nan();
     int q;
-    double r = trig_reduce((double)x, &q);
-    double c = (q & 1) ? ksin(r) : kcos(r);
+    double r = trig_reduce<K>((double)x, &q);
+    double c = (q & 1) ? ksin<K>(r) : kcos<K>(r);
     if (((q + 1) & 2) != 0) c = -c;
     return (float)c;
 }
 
-RM_HD float tan_f(float x) {
+template <class K>
+RM_HD float tan_k(float x) {
     if (f_isnan(x) || f_isinf(x)) return f_nan();
     if (x == 0.0f) return x;
     int q;
-    double r = trig_reduce((double)x, &q);
-    double s = ksin(r), c = kcos(r);
+    double r = trig_reduce<K>((double)x, &q);
+    double s = ksin<K>(r), c = kcos<K>(r);
     double t = (q & 1) ? (-c / s) : (s / c);
     return (float)t;
 }
 
+// scene-code built-ins (foldable) and the pipeline's RNG versions (table-driven)
+RM_HD float sin_f(float x) { return sin_k<TrigLit>(x); }
+RM_HD float cos_f(float x) { return cos_k<TrigLit>(x); }
+RM_HD float tan_f(float x) { return tan_k<TrigLit>(x); }
+RM_HD float sin_ft(float x) { return sin_k<TrigTab>(x); }
+RM_HD float cos_ft(float x) { return cos_k<TrigTab>(x); }
+RM_HD float tan_ft(float x) { return tan_k<TrigTab>(x); }
+
 // ---------------------------------------------------------------- log2 / exp2 in binary64
+// Coefficients from literals (LeLit: foldable, scene code) or from a table (LeTab: pipeline code on
+// the device, constant-bank operands) - see TrigLit / TrigTab above; same values, same results.
+#define RM_LE_COEFFS                                                                                       \
+    1.0 / 25.0, 1.0 / 23.0, 1.0 / 21.0, 1.0 / 19.0, 1.0 / 17.0, 1.0 / 15.0, 1.0 / 13.0, 1.0 / 11.0,      /*  0 atanh series */ \
+    1.0 / 9.0, 1.0 / 7.0, 1.0 / 5.0, 1.0 / 3.0,                                                            \
+    1.44269504088896338700e+00,                                                                /* 12 1/ln2 */ \
+    1.41421356237309514547,                                                                    /* 13 sqrt2 */ \
+    6.93147180559945286227e-01,                                                                /* 14 ln2   */ \
+    1.0 / 87178291200.0, 1.0 / 6227020800.0, 1.0 / 479001600.0, 1.0 / 39916800.0, 1.0 / 3628800.0, /* 15 1/14! .. */ \
+    1.0 / 362880.0, 1.0 / 40320.0, 1.0 / 5040.0, 1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0     /* .. 26 1/3! */
+#if RM_DEVICE_CODE
+__device__ __constant__ double rm_le_tab[27] = {RM_LE_COEFFS};
+#else
+static const double rm_le_tab[27] = {RM_LE_COEFFS};
+#endif
+struct LeTab { static RM_HD double at(int i) { return rm_le_tab[i]; } };
+struct LeLit {
+    static RM_HD double at(int i) {
+        const double v[27] = {RM_LE_COEFFS};
+        return v[i];
+    }
+};
+
 // log2(x) for finite x > 0 (denormal floats promoted to double are normal doubles).
-RM_HD double dlog2_pos(double x) {
+template <class K>
+RM_HD double dlog2_pos_k(double x) {
     long long b = d2ll(x);
     int e = (int)((b >> 52) & 0x7ff) - 1023;
     long long mb = (b & 0x000fffffffffffffLL) | 0x3ff0000000000000LL;
     double m = ll2d(mb);                                  // [1,2)
-    if (m > 1.41421356237309514547) { m = m * 0.5; e += 1; }
+    if (m > K::at(13)) { m = m * 0.5; e += 1; }
     double f = m - 1.0;                                   // [-0.2929, 0.4142]
     double s = f / (2.0 + f);                             // |s| <= 0.1716
     double z = s * s;
     // atanh series: ln(m) = 2s(1 + z/3 + z^2/5 + ... ), 12 terms => < 1e-18 truncation
-    double p = 1.0 / 25.0;
-    p = dfma(z, p, 1.0 / 23.0);
-    p = dfma(z, p, 1.0 / 21.0);
-    p = dfma(z, p, 1.0 / 19.0);
-    p = dfma(z, p, 1.0 / 17.0);
-    p = dfma(z, p, 1.0 / 15.0);
-    p = dfma(z, p, 1.0 / 13.0);
-    p = dfma(z, p, 1.0 / 11.0);
-    p = dfma(z, p, 1.0 / 9.0);
-    p = dfma(z, p, 1.0 / 7.0);
-    p = dfma(z, p, 1.0 / 5.0);
-    p = dfma(z, p, 1.0 / 3.0);
+    double p = K::at(0);
+    p = dfma(z, p, K::at(1));
+    p = dfma(z, p, K::at(2));
+    p = dfma(z, p, K::at(3));
+    p = dfma(z, p, K::at(4));
+    p = dfma(z, p, K::at(5));
+    p = dfma(z, p, K::at(6));
+    p = dfma(z, p, K::at(7));
+    p = dfma(z, p, K::at(8));
+    p = dfma(z, p, K::at(9));
+    p = dfma(z, p, K::at(10));
+    p = dfma(z, p, K::at(11));
     p = dfma(z, p, 1.0);
     double lnm = 2.0 * s * p;
-    const double INV_LN2 = 1.44269504088896338700e+00;
-    return dfma(lnm, INV_LN2, (double)e);
+    return dfma(lnm, K::at(12), (double)e);
 }
+RM_HD double dlog2_pos(double x) { return dlog2_pos_k<LeLit>(x); }
 
 // 2^t for any double t; result is a double that converts to the wanted float
 // (overflow -> +inf, underflow -> denormal/0 through the final conversion).
-RM_HD double dexp2(double t) {
+template <class K>
+RM_HD double dexp2_k(double t) {
     if (d_isnan(t)) return t;
     if (t > 1000.0) t = 1000.0;
     if (t < -1000.0) t = -1000.0;
     double n = drint(t);
-    double f = (t - n) * 6.93147180559945286227e-01;      // f*ln2, |f| <= 0.3466
+    double f = (t - n) * K::at(14);                       // f*ln2, |f| <= 0.3466
     // exp(f) Taylor to degree 14 (0.3466^15/15! ~ 1e-19)
-    double p = 1.0 / 87178291200.0;
-    p = dfma(f, p, 1.0 / 6227020800.0);
-    p = dfma(f, p, 1.0 / 479001600.0);
-    p = dfma(f, p, 1.0 / 39916800.0);
-    p = dfma(f, p, 1.0 / 3628800.0);
-    p = dfma(f, p, 1.0 / 362880.0);
-    p = dfma(f, p, 1.0 / 40320.0);
-    p = dfma(f, p, 1.0 / 5040.0);
-    p = dfma(f, p, 1.0 / 720.0);
-    p = dfma(f, p, 1.0 / 120.0);
-    p = dfma(f, p, 1.0 / 24.0);
-    p = dfma(f, p, 1.0 / 6.0);
+    double p = K::at(15);
+    p = dfma(f, p, K::at(16));
+    p = dfma(f, p, K::at(17));
+    p = dfma(f, p, K::at(18));
+    p = dfma(f, p, K::at(19));
+    p = dfma(f, p, K::at(20));
+    p = dfma(f, p, K::at(21));
+    p = dfma(f, p, K::at(22));
+    p = dfma(f, p, K::at(23));
+    p = dfma(f, p, K::at(24));
+    p = dfma(f, p, K::at(25));
+    p = dfma(f, p, K::at(26));
     p = dfma(f, p, 0.5);
     p = dfma(f, p, 1.0);
     p = dfma(f, p, 1.0);
     long long sb = ((long long)((int)n + 1023)) << 52;    // |n| <= 1000 so exponent is in range
     return p * ll2d(sb);
 }
+RM_HD double dexp2(double t) { return dexp2_k<LeLit>(t); }
+
+// table-driven versions for pipeline code (RNG, shading, display): never constant arguments
+RM_HD float log_ft(float x) {
+    if (f_isnan(x) || x < 0.0f) return f_nan();
+    if (x == 0.0f) return -f_inf();
+    if (f_isinf(x)) return x;
+    return (float)(dlog2_pos_k<LeTab>((double)x) * LeTab::at(14));
+}
+RM_HD float exp_ft(float x) { return (float)dexp2_k<LeTab>((double)x * LeTab::at(12)); }
 
 RM_HD float log2_f(float x) {
     if (f_isnan(x) || x < 0.0f) return f_nan();
@@ -230,7 +299,8 @@ RM_HD float exp_f(float x) { return (float)dexp2((double)x * 1.44269504088896338
 // being a square (schlick(), raymarcher.frag:173, with n1 < n2), which is what GPU compilers
 // deliver by strength-reducing constant integer exponents.  Pinned: C99 powf semantics - a
 // negative base with an integral exponent gives +-|x|^y, otherwise NaN; pow(x,0)=1, pow(0,y>0)=0.
-RM_HD float pow_f(float x, float y) {
+template <class K>
+RM_HD float pow_k(float x, float y) {
     if (f_isnan(x) || f_isnan(y)) return f_nan();
     if (y == 0.0f) return 1.0f;
     bool negate = false;
@@ -251,9 +321,11 @@ RM_HD float pow_f(float x, float y) {
     else if (f_isinf(y)) {
         bool grow = (x > 1.0f) == (y > 0.0f);
         r = grow ? f_inf() : 0.0f;
-    } else r = (float)dexp2((double)y * dlog2_pos((double)x));
+    } else r = (float)dexp2_k<K>((double)y * dlog2_pos_k<K>((double)x));
     return negate ? -r : r;
 }
+RM_HD float pow_f(float x, float y) { return pow_k<LeLit>(x, y); }
+RM_HD float pow_ft(float x, float y) { return pow_k<LeTab>(x, y); }
 
 // ---------------------------------------------------------------- inverse trigonometric
 // atan for a double argument, result in (-pi/2, pi/2).

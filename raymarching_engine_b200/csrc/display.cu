@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(256) rm_display_kernel(const float4* __restric
         for (float xo = -kernelSize; xo <= kernelSize; xo = g_add(xo, 1.0f)) {
             const vec2 offset(xo, y);
             const vec2 texOffset = offset / vec2((float)W, (float)H);
-            const float factor = g_mul(norm, exp(-g_div(dot(offset, offset), twoSigma2)));
+            const float factor = g_mul(norm, rmx::exp_ft(-g_div(dot(offset, offset), twoSigma2)));   // exp of the exact policy, table-driven coefficients
             sampleCount = g_add(sampleCount, factor);
             const vec2 uv = texcoord + texOffset;
             // NEAREST + REPEAT: texel = floor(uv * size) mod size
@@ -80,7 +80,9 @@ __global__ void __launch_bounds__(256) rm_display_kernel(const float4* __restric
         }
     }
     avg /= sampleCount;
-    const vec4 frag = pow(vec4(vec3(avg.x, avg.y, avg.z) * brightness, 1.0f), vec4(g_div(1.0f, 2.2f)));   // :54
+    const vec4 base(vec3(avg.x, avg.y, avg.z) * brightness, 1.0f);
+    const float ig = g_div(1.0f, 2.2f);
+    const vec4 frag(rmx::pow_ft(base.x, ig), rmx::pow_ft(base.y, ig), rmx::pow_ft(base.z, ig), rmx::pow_ft(base.w, ig));   // :54
     unsigned char b[4];
     for (int cpt = 0; cpt < 4; cpt++) {
         float v = frag[cpt];

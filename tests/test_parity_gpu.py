@@ -475,3 +475,35 @@ def test_degenerate_draws(ctx):
         s.reflectionIterationCounts = counts
         got, planes, acc, want = _render_both(ctx, "guide", s)
         _assert_bit_exact(got, planes, acc, want)
+
+
+TEXCOORD_SCENE = """
+// a pure scene that reads the per-pixel input `texcoord` inside sdf(): legal in the reference (the
+// splice point follows the varying, raymarcher.frag:69/146) and must survive the wavefront march,
+// where a lane's pixel changes every time it is refilled
+float sdf(vec3 p) {
+  float wobble = 0.3 * sin(40.0 * texcoord.x) * cos(25.0 * texcoord.y);
+  return length(p - vec3(0.0, 0.0, 4.0)) - 1.0 - wobble;
+}
+"""
+
+
+def test_scene_reading_texcoord_wavefront_equals_megakernel(ctx):
+    mega = rm.load_render_job_context(device=0, pipeline="megakernel")
+    try:
+        outs = []
+        for c in (ctx, mega):
+            s = rm.default_schema(TEXCOORD_SCENE, {}, width=150, height=90, renderMode="full", frameid=9600)
+            s.lights = [rm.default_light()]
+            s.lights[0].position = (2.0, 2.0, 0.0)
+            rm.reset_halton()
+            fb = c.fbo.create(150, 90, 9600)
+            got = rm.run_job(s, c)
+            assert got["success"], got["why"]
+            outs.append((fb.read("color"), fb.read("depth"), got["rgba8"].copy()))
+        np.testing.assert_array_equal(_canon(outs[0][0]), _canon(outs[1][0]))
+        np.testing.assert_array_equal(_canon(outs[0][1]), _canon(outs[1][1]))
+        np.testing.assert_array_equal(outs[0][2], outs[1][2])
+        assert len(np.unique(outs[0][2].reshape(-1, 4), axis=0)) > 50      # the wobble really shapes the image
+    finally:
+        mega.close()
