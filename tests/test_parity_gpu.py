@@ -61,7 +61,8 @@ def test_preview_bit_exact_all_scenes(ctx, name):
     _assert_bit_exact(got, planes, acc, want)
 
 
-@pytest.mark.parametrize("name", ["guide", "sphere-grid", "menger-sponge", "tree"])
+@pytest.mark.parametrize("name", ["guide", "sphere-grid", "menger-sponge", "tree", "fractal1", "smooth-tree", "rotation-fractal",
+                                  "inline-default", "mandelbulb"])
 def test_full_bit_exact(ctx, name):
     got, planes, acc, want = _render_both(ctx, name, _schema(name, 96, 54, "full", lights=1))
     _assert_bit_exact(got, planes, acc, want)
@@ -532,3 +533,37 @@ def test_fast_flavour_full_mode_converges_to_exact(ctx):
         assert abs(imgs[0].mean() - imgs[1].mean()) < 1.0      # no brightness bias
     finally:
         fast.close()
+
+
+def test_render_frames_two_contexts_equals_run_job(ctx):
+    """Frames dealt round-robin to two contexts of the same GPU (own streams, module instances and ray
+    planes; what bench.py does) come back in order and identical to blocking single-context jobs."""
+    import math
+    other = rm.load_render_job_context(device=0)
+    try:
+        def schemas(base):
+            out = []
+            for k in range(7):
+                s = _schema("guide", 120, 68, "preview" if k % 3 else "full", lights=0 if k % 3 else 1, frameid=base + k)
+                th = 0.3 * k
+                s.camera.position = (10.0 * math.sin(th), 0.0, 10.0 - 10.0 * math.cos(th))
+                c, sn = math.cos(-th), math.sin(-th)
+                s.camera.rotation = (c, 0, -sn, 0, 0, 1, 0, 0, sn, 0, c, 0, 0, 0, 0, 1)
+                out.append(s)
+            return out
+        rm.reset_halton()
+        want = []
+        for s in schemas(9700):
+            r = rm.run_job(s, ctx)
+            assert r["success"]
+            want.append((r["rgba8"].copy(), r["depth"].copy()))
+        rm.reset_halton()
+        seen = []
+        for i, r in rm.render_frames(schemas(9800), [ctx, other], depth=2):
+            assert r["success"]
+            np.testing.assert_array_equal(r["rgba8"], want[i][0])
+            np.testing.assert_array_equal(_canon(r["depth"]), _canon(want[i][1]))
+            seen.append(i)
+        assert seen == list(range(7))
+    finally:
+        other.close()
