@@ -172,8 +172,26 @@ RM_HD float tan_k(float x) {
     int q;
     double r = trig_reduce<K>((double)x, &q);
     double s = ksin<K>(r), c = kcos<K>(r);
-    double t = (q & 1) ? (-c / s) : (s / c);
-    return (float)t;
+    // one division: -c/s in odd quadrants, s/c in even ones (operands selected first; same quotient bits)
+    const double num = (q & 1) ? -c : s;
+    const double den = (q & 1) ? s : c;
+    return (float)(num / den);
+}
+
+// sin and cos of the same argument with one reduction and one pair of polynomials (Box-Muller);
+// each result is bit-identical to sin_k / cos_k
+template <class K>
+RM_HD void sincos_k(float x, float* sn, float* cs) {
+    if (f_isnan(x) || f_isinf(x)) { *sn = f_nan(); *cs = f_nan(); return; }
+    int q;
+    double r = trig_reduce<K>((double)x, &q);
+    const double ps = ksin<K>(r), pc = kcos<K>(r);
+    double s = (q & 1) ? pc : ps;
+    if (q & 2) s = -s;
+    double c = (q & 1) ? ps : pc;
+    if (((q + 1) & 2) != 0) c = -c;
+    *sn = (x == 0.0f) ? x : (float)s;
+    *cs = (float)c;
 }
 
 // scene-code built-ins (foldable) and the pipeline's RNG versions (table-driven)
@@ -183,6 +201,7 @@ RM_HD float tan_f(float x) { return tan_k<TrigLit>(x); }
 RM_HD float sin_ft(float x) { return sin_k<TrigTab>(x); }
 RM_HD float cos_ft(float x) { return cos_k<TrigTab>(x); }
 RM_HD float tan_ft(float x) { return tan_k<TrigTab>(x); }
+RM_HD void sincos_ft(float x, float* sn, float* cs) { sincos_k<TrigTab>(x, sn, cs); }
 
 // ---------------------------------------------------------------- log2 / exp2 in binary64
 // Coefficients from literals (LeLit: foldable, scene code) or from a table (LeTab: pipeline code on

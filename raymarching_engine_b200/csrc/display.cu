@@ -47,35 +47,42 @@ __global__ void __launch_bounds__(256) rm_display_kernel(const float4* __restric
     const float sigma = g_mul(max(kernelSize, 1.0f), 0.3f);
     const float norm = g_div(1.0f, g_mul(g_mul(g_mul(2.0f, PI_D), sigma), sigma));
     const float twoSigma2 = g_mul(g_mul(2.0f, sigma), sigma);
+    // NEAREST + REPEAT: texel = floor(uv * size) mod size.  The wrap is a compare-and-add when the index
+    // is within one period of the range (always, for a +-16 pixel kernel on frames >= 16 pixels), an
+    // integer remainder otherwise - same result.
+    auto wrap = [](float f, int n) -> long long {
+        if (f >= -(float)n && f < 2.0f * (float)n) {
+            int v = (int)f;
+            if (v < 0) v += n;
+            else if (v >= n) v -= n;
+            return v;
+        }
+        if (fabsf(f) < 1.0e9f) { int v = (int)f % n; return v < 0 ? v + n : v; }
+        long long v = (long long)f % n;
+        return v < 0 ? v + n : v;
+    };
     for (float y = -kernelSize; y <= kernelSize; y = g_add(y, 1.0f)) {   // :42-50
+        // everything that depends on the row only, once per row (the same operations the shader repeats
+        // for every tap of the row)
+        const float texOffsetY = g_div(y, (float)H);
+        const float uvY = g_add(texcoord.y, texOffsetY);
+        const long long j = wrap(floor(g_mul(uvY, (float)H)), H);
+        // global row j -> local row (identity when this rank owns every row)
+        long long lj = j;
+        if (nRanks > 1) {
+            const long long tj = j / tileRows;
+            lj = (tj / nRanks) * tileRows + (j - tj * tileRows);
+            if (tj % nRanks != rank) lj = ly;   // not resident here (see header note)
+        }
+        const float4* __restrict__ row = color + (size_t)lj * (size_t)W;
         for (float xo = -kernelSize; xo <= kernelSize; xo = g_add(xo, 1.0f)) {
             const vec2 offset(xo, y);
-            const vec2 texOffset = offset / vec2((float)W, (float)H);
+            const float texOffsetX = g_div(xo, (float)W);
             const float factor = g_mul(norm, rmx::exp_ft(-g_div(dot(offset, offset), twoSigma2)));   // exp of the exact policy, table-driven coefficients
             sampleCount = g_add(sampleCount, factor);
-            const vec2 uv = texcoord + texOffset;
-            // NEAREST + REPEAT: texel = floor(uv * size) mod size
-            const float fi = floor(g_mul(uv.x, (float)W)), fj = floor(g_mul(uv.y, (float)H));
-            long long i, j;
-            if (fabsf(fi) < 1.0e9f && fabsf(fj) < 1.0e9f) {
-                // 32-bit wrap (the 64-bit remainder is ~100 instructions); same result
-                int ii = (int)fi % W, jj = (int)fj % H;
-                if (ii < 0) ii += W;
-                if (jj < 0) jj += H;
-                i = ii; j = jj;
-            } else {
-                i = (long long)fi; j = (long long)fj;
-                i %= W; if (i < 0) i += W;
-                j %= H; if (j < 0) j += H;
-            }
-            // global row j -> local row (identity when this rank owns every row)
-            long long lj = j;
-            if (nRanks > 1) {
-                const long long tj = j / tileRows;
-                lj = (tj / nRanks) * tileRows + (j - tj * tileRows);
-                if (tj % nRanks != rank) lj = ly;   // not resident here (see header note)
-            }
-            const float4 c = color[(size_t)lj * (size_t)W + (size_t)i];
+            const float uvX = g_add(texcoord.x, texOffsetX);
+            const long long i = wrap(floor(g_mul(uvX, (float)W)), W);
+            const float4 c = row[i];
             avg += vec4(c.x, c.y, c.z, c.w) * factor;
         }
     }
