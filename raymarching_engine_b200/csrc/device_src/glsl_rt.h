@@ -106,6 +106,29 @@ RM_HD float g_fma(float a, float b, float c) { return __builtin_fmaf(a, b, c); }
 RM_HD float g_rcp(float a) { return 1.0f / a; }
 #endif
 
+#if RM_DEVICE_CODE && defined(RM_USE_F32X2) && RM_USE_F32X2
+// Blackwell packed FP32 (FFMA2 / FADD2 / FMUL2: two IEEE round-to-nearest operations per lane per issue
+// slot, bit-identical to the scalar instructions).  The march loops are issue-bound, so the x and y
+// components of the hot vector operations travel as one f32x2 value; z stays scalar.
+#define GLSL_F32X2 1
+RM_HD unsigned long long f2_pack(float a, float b) { unsigned long long r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+RM_HD void f2_unpack(unsigned long long v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+RM_HD unsigned long long f2_fma(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r;
+}
+RM_HD unsigned long long f2_add(unsigned long long a, unsigned long long b) {
+    unsigned long long r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r;
+}
+RM_HD unsigned long long f2_sub(unsigned long long a, unsigned long long b) {
+    unsigned long long r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r;
+}
+RM_HD unsigned long long f2_mul(unsigned long long a, unsigned long long b) {
+    unsigned long long r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r;
+}
+#else
+#define GLSL_F32X2 0
+#endif
+
 #if RM_DEVICE_CODE
 RM_HD float g_min(float a, float b) { return fminf(a, b); }
 RM_HD float g_max(float a, float b) { return fmaxf(a, b); }
@@ -505,7 +528,27 @@ RM_HD float rm_c(const vec4& a, int i) { return a[i]; }
 template <class H1, class S, class H2> RM_HD vec2 rm_rep(const vec2& x, const H1& h1, const S& s, const H2& h2) {
     return vec2(rm_rep1(x.x, rm_c(h1, 0), rm_c(s, 0), rm_c(h2, 0)), rm_rep1(x.y, rm_c(h1, 1), rm_c(s, 1), rm_c(h2, 1)));
 }
-#if !GLSL_FAST && RM_DEVICE_CODE && defined(RM_FLOOR_FP_COMPONENTS) && !(defined(RM_PIN_ALT) && RM_PIN_ALT)
+#if !GLSL_FAST && GLSL_F32X2 && !(defined(RM_PIN_ALT) && RM_PIN_ALT) && !(defined(RM_FLOOR_FP_COMPONENTS) && RM_FLOOR_FP_COMPONENTS > 0)
+// exact policy, packed: the same operations as rm_rep1 on every component - add, multiply by the
+// correctly rounded reciprocal, floor, fused multiply-add, subtract - with x and y sharing FADD2 /
+// FMUL2 / FFMA2 instructions (IEEE round-to-nearest per element, so the bits are those of rm_rep1)
+template <class H1, class S, class H2> RM_HD vec3 rm_rep(const vec3& x, const H1& h1, const S& s, const H2& h2) {
+    const float sx = rm_c(s, 0), sy = rm_c(s, 1), sz = rm_c(s, 2);
+    const float rx = g_rcp(sx), ry = g_rcp(sy), rz = g_rcp(sz);
+    const unsigned long long A = f2_add(f2_pack(x.x, x.y), f2_pack(rm_c(h1, 0), rm_c(h1, 1)));
+    const unsigned long long Q = f2_mul(A, f2_pack(rx, ry));
+    float qx, qy;
+    f2_unpack(Q, qx, qy);
+    const unsigned long long F = f2_pack(g_floor(qx), g_floor(qy));
+    const unsigned long long Mxy = f2_fma(f2_pack(-sx, -sy), F, A);
+    const unsigned long long E = f2_sub(Mxy, f2_pack(rm_c(h2, 0), rm_c(h2, 1)));
+    vec3 out;
+    f2_unpack(E, out.x, out.y);
+    out.z = rm_rep1(x.z, rm_c(h1, 2), sz, rm_c(h2, 2));
+    (void)rz;
+    return out;
+}
+#elif !GLSL_FAST && RM_DEVICE_CODE && defined(RM_FLOOR_FP_COMPONENTS) && !(defined(RM_PIN_ALT) && RM_PIN_ALT)
 RM_HD float rm_rep1_fp(float x, float h1, float s, float h2) { return g_sub(mod_fp(g_add(x, h1), s), h2); }
 template <class H1, class S, class H2> RM_HD vec3 rm_rep(const vec3& x, const H1& h1, const S& s, const H2& h2) {
     return vec3(RM_FLOOR_FP_COMPONENTS > 0 ? rm_rep1_fp(x.x, rm_c(h1, 0), rm_c(s, 0), rm_c(h2, 0)) : rm_rep1(x.x, rm_c(h1, 0), rm_c(s, 0), rm_c(h2, 0)),
@@ -513,10 +556,31 @@ template <class H1, class S, class H2> RM_HD vec3 rm_rep(const vec3& x, const H1
                 RM_FLOOR_FP_COMPONENTS > 2 ? rm_rep1_fp(x.z, rm_c(h1, 2), rm_c(s, 2), rm_c(h2, 2)) : rm_rep1(x.z, rm_c(h1, 2), rm_c(s, 2), rm_c(h2, 2)));
 }
 #else
+#if GLSL_FAST && GLSL_F32X2
+// packed (x, y) + scalar z version of the centred remainder
+template <class H1, class S, class H2> RM_HD vec3 rm_rep(const vec3& x, const H1& h1, const S& s, const H2& h2) {
+    const float s0 = rm_c(s, 0), a0 = rm_c(h1, 0), b0 = rm_c(h2, 0);
+    const bool uniform = s0 == rm_c(s, 1) && s0 == rm_c(s, 2) && a0 == rm_c(h1, 1) && a0 == rm_c(h1, 2) && b0 == rm_c(h2, 1) && b0 == rm_c(h2, 2);
+    if (uniform && a0 == b0 && b0 == 0.5f * s0 && s0 > 0.0f && s0 < 1e30f) {
+        const float M = 12582912.0f, rs = 1.0f / s0;
+        const unsigned long long Y = f2_pack(x.x, x.y);
+        const unsigned long long R = f2_add(f2_fma(Y, f2_pack(rs, rs), f2_pack(M, M)), f2_pack(-M, -M));
+        const unsigned long long Q = f2_fma(f2_pack(-s0, -s0), R, Y);
+        vec3 out;
+        f2_unpack(Q, out.x, out.y);
+        const float rz = __fadd_rn(__fmaf_rn(x.z, rs, M), -M);
+        out.z = __fmaf_rn(-s0, rz, x.z);
+        return out;
+    }
+    return vec3(rm_rep1(x.x, rm_c(h1, 0), rm_c(s, 0), rm_c(h2, 0)), rm_rep1(x.y, rm_c(h1, 1), rm_c(s, 1), rm_c(h2, 1)),
+                rm_rep1(x.z, rm_c(h1, 2), rm_c(s, 2), rm_c(h2, 2)));
+}
+#else
 template <class H1, class S, class H2> RM_HD vec3 rm_rep(const vec3& x, const H1& h1, const S& s, const H2& h2) {
     return vec3(rm_rep1(x.x, rm_c(h1, 0), rm_c(s, 0), rm_c(h2, 0)), rm_rep1(x.y, rm_c(h1, 1), rm_c(s, 1), rm_c(h2, 1)),
                 rm_rep1(x.z, rm_c(h1, 2), rm_c(s, 2), rm_c(h2, 2)));
 }
+#endif
 #endif
 template <class H1, class S, class H2> RM_HD vec4 rm_rep(const vec4& x, const H1& h1, const S& s, const H2& h2) {
     return vec4(rm_rep1(x.x, rm_c(h1, 0), rm_c(s, 0), rm_c(h2, 0)), rm_rep1(x.y, rm_c(h1, 1), rm_c(s, 1), rm_c(h2, 1)),

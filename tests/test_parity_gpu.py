@@ -34,6 +34,9 @@ def _render_both(ctx, name, schema):
     fb = ctx.fbo.create(schema.render.width, schema.render.height, schema.render.frameid)
     got = rm.run_job(schema, ctx)
     assert got["success"], got["why"]
+    # run_job hands out views of the context's pinned readback buffers: copy, so that the result
+    # outlives the next job and a context.close()
+    got = dict(got, rgba8=got["rgba8"].copy(), depth=got["depth"].copy())
     planes = {p: fb.read(p) for p in ("color", "normalAndDofRadius", "albedoAndDepth", "depth")}
     acc, want = pyoracle.run_job(name, schema)
     return got, planes, acc, want
