@@ -456,6 +456,7 @@ def run_b200(args):
     evals_solo, _px_solo = ctxs[0].counters(reset=True)
     nctx = nctx_saved
     fp32_measured = ctxs[0].measure_fp32_peak(0.5)
+    fp32x2_measured = ctxs[0].measure_fp32_peak(0.3, packed=True)
     sm_count = torch.cuda.get_device_properties(local).multi_processor_count
     sm_max = clocks.get("sm_max_mhz") or 1965.0
     nominal_peak = sm_count * 128 * 2 * sm_max * 1e6 / 1e12
@@ -477,7 +478,7 @@ def run_b200(args):
     roofline = {
         "bound": "fp32", "achieved": achieved, "peak": nominal_peak, "unit": "TFLOP/s", "frac": achieved / nominal_peak, "traffic": traffic,
         "peak_source": f"derived: {sm_count} SMs x 128 FP32 lanes x 2 x {sm_max:.0f} MHz (MEASURED_PEAKS.json has no FP32 figure; BASELINE.md section 2)",
-        "peak_measured_ffma": fp32_measured, "frac_of_measured_ffma": achieved / fp32_measured if fp32_measured else None,
+        "peak_measured_ffma": fp32_measured, "peak_measured_ffma2_packed": fp32x2_measured, "frac_of_measured_ffma": achieved / fp32_measured if fp32_measured else None,
         "kernel": hot_kernel, "kernel_launches_per_step": hot_launches / max(args.steps, 1),
         "kernel_ms_per_step": 1e3 * kernel_s / max(args.steps, 1), "kernel_ms_avg": 1e3 * kernel_s / max(hot_launches, 1),
         "kernel_share_of_step": min(1.0, kernel_s / (total_ms * 1e-3)),

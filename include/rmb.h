@@ -202,6 +202,9 @@ rmb_status rmb_compile_only(const char* scene_glsl, size_t scene_len, int flavou
 /* FP32 FMA throughput of this GPU in TFLOP/s (register-only FFMA kernel, best of `seconds` of
  * launches): the roofline denominator for this FP32-bound path. */
 rmb_status rmb_measure_fp32_peak(rmb_ctx* ctx, double seconds, double* tflops);
+/* the same probe issued as packed FFMA2 (fma.rn.f32x2, 4 flop per lane-instruction): tells whether
+ * packing raises the FP32 ceiling or only saves issue slots */
+rmb_status rmb_measure_fp32x2_peak(rmb_ctx* ctx, double seconds, double* tflops);
 /* host-only helper: rows with global index < g owned by `rank` under the round-robin row-tile
  * deal (tile t -> rank t % n_ranks).  -1 on bad arguments.  Needs no GPU. */
 int rmb_owned_rows_below(int g, int height, int tile_rows, int n_ranks, int rank);

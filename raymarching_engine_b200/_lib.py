@@ -24,7 +24,7 @@ EXPORTED_SYMBOLS = [
     "rmb_uniform_matrix4", "rmb_fb_acquire", "rmb_fb_release", "rmb_fb_local_rows", "rmb_fb_global_row",
     "rmb_render_sample", "rmb_present", "rmb_present_device", "rmb_present_async", "rmb_present_wait", "rmb_fb_device_ptr", "rmb_fb_plane_bytes",
     "rmb_fb_read", "rmb_fb_write", "rmb_fb_copy_to_device", "rmb_counters_read", "rmb_probe", "rmb_compile_only", "rmb_host_alloc", "rmb_device_alloc", "rmb_device_free",
-    "rmb_host_free", "rmb_measure_fp32_peak", "rmb_owned_rows_below",
+    "rmb_host_free", "rmb_measure_fp32_peak", "rmb_measure_fp32x2_peak", "rmb_owned_rows_below",
 ]
 
 
@@ -84,6 +84,7 @@ def _load() -> C.CDLL:
         "rmb_probe": (i, [vp, vp, vp, i, vp]),
         "rmb_compile_only": (i, [cp, sz, i, C.POINTER(SpecUniform), i, cp, sz, vp, sz, C.POINTER(sz), cp, sz]),
         "rmb_measure_fp32_peak": (i, [vp, C.c_double, C.POINTER(C.c_double)]),
+        "rmb_measure_fp32x2_peak": (i, [vp, C.c_double, C.POINTER(C.c_double)]),
         "rmb_owned_rows_below": (i, [i, i, i, i, i]),
         "rmb_host_alloc": (vp, [sz]),
         "rmb_device_alloc": (vp, [vp, sz]),

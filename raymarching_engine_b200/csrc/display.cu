@@ -144,6 +144,30 @@ __global__ void __launch_bounds__(256) rm_fp32_peak_kernel(float* out, int iters
     out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
 }
 
+// The same probe with Blackwell's packed FFMA2 (fma.rn.f32x2: two FMAs per lane per instruction): shows
+// whether packing raises the FP32 ceiling itself or only saves issue slots.  4 flop per FFMA2.
+__global__ void __launch_bounds__(256) rm_fp32x2_peak_kernel(float* out, int iters, float a, float b) {
+    unsigned long long x[8], aa, bb;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(aa) : "f"(a));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(bb) : "f"(b));
+    for (int k = 0; k < 8; k++) { float v = threadIdx.x + k; asm("mov.b64 %0, {%1, %1};" : "=l"(x[k]) : "f"(v)); }
+#pragma unroll 1
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) asm("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(x[j]) : "l"(aa), "l"(bb));
+        }
+    }
+    float s = 0.0f;
+    for (int k = 0; k < 8; k++) { float lo, hi; asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(x[k])); s += lo + hi; }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+extern "C" cudaError_t rmb_launch_fp32x2_peak(float* scratch, int blocks, int iters, cudaStream_t stream) {
+    rm_fp32x2_peak_kernel<<<blocks, 256, 0, stream>>>(scratch, iters, 0.999999f, 1e-7f);
+    return cudaGetLastError();
+}
+
 // Launches the probe with `blocks` blocks of 256 threads; flops = blocks*256*iters*16*8*2.
 extern "C" cudaError_t rmb_launch_fp32_peak(float* scratch, int blocks, int iters, cudaStream_t stream) {
     rm_fp32_peak_kernel<<<blocks, 256, 0, stream>>>(scratch, iters, 0.999999f, 1e-7f);

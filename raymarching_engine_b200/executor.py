@@ -194,9 +194,10 @@ class RenderJobContext:                  # RenderJobExecutor.tsx:32-54
         if L.rmb_present_wait(self.handle, fb.handle) != _lib.RMB_OK:
             raise RuntimeError(self.last_error())
 
-    def measure_fp32_peak(self, seconds: float = 0.5) -> float:
+    def measure_fp32_peak(self, seconds: float = 0.5, packed: bool = False) -> float:
         out = C.c_double(0.0)
-        if L.rmb_measure_fp32_peak(self.handle, seconds, C.byref(out)) != _lib.RMB_OK:
+        fn = L.rmb_measure_fp32x2_peak if packed else L.rmb_measure_fp32_peak
+        if fn(self.handle, seconds, C.byref(out)) != _lib.RMB_OK:
             raise RuntimeError(self.last_error())
         return out.value
 
