@@ -111,20 +111,20 @@ RM_HD float g_rcp(float a) { return 1.0f / a; }
 // slot, bit-identical to the scalar instructions).  The march loops are issue-bound, so the x and y
 // components of the hot vector operations travel as one f32x2 value; z stays scalar.
 #define GLSL_F32X2 1
-RM_HD unsigned long long f2_pack(float a, float b) { unsigned long long r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
-RM_HD void f2_unpack(unsigned long long v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
-RM_HD unsigned long long f2_fma(unsigned long long a, unsigned long long b, unsigned long long c) {
-    unsigned long long r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r;
+// the CUDA 12.9 sm_100 builtins behind __ffma2_rn & co (crt/sm_100_rt.hpp), declared here because NVRTC
+// sees no CUDA headers; unlike inline PTX the compiler understands them (broadcast / immediate operands)
+extern "C" {      // (re-declared in every namespace this header creates; same C-linkage entities)
+__device__ __device_builtin__ float2 __ffma2_rn_impl(float2 x, float2 y, float2 z);
+__device__ __device_builtin__ float2 __fadd2_rn_impl(float2 x, float2 y);
+__device__ __device_builtin__ float2 __fmul2_rn_impl(float2 x, float2 y);
 }
-RM_HD unsigned long long f2_add(unsigned long long a, unsigned long long b) {
-    unsigned long long r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r;
-}
-RM_HD unsigned long long f2_sub(unsigned long long a, unsigned long long b) {
-    unsigned long long r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r;
-}
-RM_HD unsigned long long f2_mul(unsigned long long a, unsigned long long b) {
-    unsigned long long r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r;
-}
+typedef float2 f2_t;
+RM_HD f2_t f2_pack(float a, float b) { return make_float2(a, b); }
+RM_HD void f2_unpack(f2_t v, float& a, float& b) { a = v.x; b = v.y; }
+RM_HD f2_t f2_fma(f2_t a, f2_t b, f2_t c) { return __ffma2_rn_impl(a, b, c); }
+RM_HD f2_t f2_add(f2_t a, f2_t b) { return __fadd2_rn_impl(a, b); }
+RM_HD f2_t f2_sub(f2_t a, f2_t b) { return __fadd2_rn_impl(a, make_float2(-b.x, -b.y)); }   // a + (-b) == a - b bit for bit
+RM_HD f2_t f2_mul(f2_t a, f2_t b) { return __fmul2_rn_impl(a, b); }
 #else
 #define GLSL_F32X2 0
 #endif
@@ -535,13 +535,13 @@ template <class H1, class S, class H2> RM_HD vec2 rm_rep(const vec2& x, const H1
 template <class H1, class S, class H2> RM_HD vec3 rm_rep(const vec3& x, const H1& h1, const S& s, const H2& h2) {
     const float sx = rm_c(s, 0), sy = rm_c(s, 1), sz = rm_c(s, 2);
     const float rx = g_rcp(sx), ry = g_rcp(sy), rz = g_rcp(sz);
-    const unsigned long long A = f2_add(f2_pack(x.x, x.y), f2_pack(rm_c(h1, 0), rm_c(h1, 1)));
-    const unsigned long long Q = f2_mul(A, f2_pack(rx, ry));
+    const f2_t A = f2_add(f2_pack(x.x, x.y), f2_pack(rm_c(h1, 0), rm_c(h1, 1)));
+    const f2_t Q = f2_mul(A, f2_pack(rx, ry));
     float qx, qy;
     f2_unpack(Q, qx, qy);
-    const unsigned long long F = f2_pack(g_floor(qx), g_floor(qy));
-    const unsigned long long Mxy = f2_fma(f2_pack(-sx, -sy), F, A);
-    const unsigned long long E = f2_sub(Mxy, f2_pack(rm_c(h2, 0), rm_c(h2, 1)));
+    const f2_t F = f2_pack(g_floor(qx), g_floor(qy));
+    const f2_t Mxy = f2_fma(f2_pack(-sx, -sy), F, A);
+    const f2_t E = f2_sub(Mxy, f2_pack(rm_c(h2, 0), rm_c(h2, 1)));
     vec3 out;
     f2_unpack(E, out.x, out.y);
     out.z = rm_rep1(x.z, rm_c(h1, 2), sz, rm_c(h2, 2));
@@ -563,9 +563,9 @@ template <class H1, class S, class H2> RM_HD vec3 rm_rep(const vec3& x, const H1
     const bool uniform = s0 == rm_c(s, 1) && s0 == rm_c(s, 2) && a0 == rm_c(h1, 1) && a0 == rm_c(h1, 2) && b0 == rm_c(h2, 1) && b0 == rm_c(h2, 2);
     if (uniform && a0 == b0 && b0 == 0.5f * s0 && s0 > 0.0f && s0 < 1e30f) {
         const float M = 12582912.0f, rs = 1.0f / s0;
-        const unsigned long long Y = f2_pack(x.x, x.y);
-        const unsigned long long R = f2_add(f2_fma(Y, f2_pack(rs, rs), f2_pack(M, M)), f2_pack(-M, -M));
-        const unsigned long long Q = f2_fma(f2_pack(-s0, -s0), R, Y);
+        const f2_t Y = f2_pack(x.x, x.y);
+        const f2_t R = f2_add(f2_fma(Y, f2_pack(rs, rs), f2_pack(M, M)), f2_pack(-M, -M));
+        const f2_t Q = f2_fma(f2_pack(-s0, -s0), R, Y);
         vec3 out;
         f2_unpack(Q, out.x, out.y);
         const float rz = __fadd_rn(__fmaf_rn(x.z, rs, M), -M);
