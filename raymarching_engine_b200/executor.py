@@ -40,6 +40,13 @@ class Program:
     def source(self) -> str:
         return L.rmb_program_source(self.handle).decode()
 
+    def is_dual(self) -> bool:
+        """True when the program marches two rays per lane with packed FP32 (glsl_pk.h)"""
+        return bool(L.rmb_program_is_dual(self.handle))
+
+    def dual_log(self) -> str:
+        return (L.rmb_program_dual_log(self.handle) or b"").decode()
+
     def kernel_attr(self, kernel: int):
         r, l = C.c_int(-1), C.c_int(-1)
         L.rmb_program_kernel_attr(self.handle, kernel, C.byref(r), C.byref(l))
