@@ -30,7 +30,13 @@ SCENES = ["guide", "fractal1", "menger-sponge", "tree", "smooth-tree", "rotation
 
 
 def scene_source(name: str) -> str:
-    return (ROOT / "scenes" / f"{name}.glsl").read_text()
+    """scenes/ holds the workloads bench.py and smoke() render; the reference's other example scenes are
+    parity-test fixtures only and live under tests/fixtures/scenes/ (see scenes/README.md)."""
+    for d in (ROOT / "scenes", ROOT / "tests" / "fixtures" / "scenes"):
+        p = d / f"{name}.glsl"
+        if p.exists():
+            return p.read_text()
+    raise FileNotFoundError(name)
 
 
 @pytest.fixture(scope="session")

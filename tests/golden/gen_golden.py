@@ -32,7 +32,7 @@ CASES = {
 def make_case(rm, name):
     import math
     scene, W, H, mode, lights, spp, extra = CASES[name]
-    src = (ROOT / "scenes" / f"{scene}.glsl").read_text()
+    src = next(d / f"{scene}.glsl" for d in (ROOT / "scenes", ROOT / "tests" / "fixtures" / "scenes") if (d / f"{scene}.glsl").exists()).read_text()
     s = rm.default_schema(src, rm.default_custom_settings(src), width=W, height=H, renderMode=mode, samplesPerPixel=spp, frameid=1)
     s.lights = [rm.default_light() for _ in range(lights)]
     if lights > 1:
