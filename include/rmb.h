@@ -197,14 +197,30 @@ rmb_status rmb_fb_write(rmb_ctx* ctx, rmb_fb* fb, int which, const void* host, s
 rmb_status rmb_fb_copy_to_device(rmb_ctx* ctx, rmb_fb* fb, int which, void* dst_device, size_t bytes);
 /* out[0] = SDF evaluations executed, out[1] = pixel-samples rendered, since the last reset */
 rmb_status rmb_counters_read(rmb_ctx* ctx, uint64_t out[2], int reset);
+/* the same plus out[2] = how many of out[0] took the far-field shortcut of a carved scene (below) */
+rmb_status rmb_counters_read3(rmb_ctx* ctx, uint64_t out[3], int reset);
 /* evaluates the scene's sdf() and material functions at n points: in n*3 floats, out n*17 floats
  * (diffuse rgb, specular rgb, roughness, subsurface, subsurfaceColor rgb, IOR, emission rgb, sdf, 0) */
 rmb_status rmb_probe(rmb_ctx* ctx, rmb_program* prog, const float* points_xyz, int n, float* out17);
+/* Far-field shortcut ("carve").  When the scene's sdf() has the form max(A, -M) with M a union of
+ * `length(..) - K` shapes whose K do not depend on the position (the reference's default scene,
+ * client/public/examples/guide.glsl:91-102, and its start-up placeholder, client/src/index.tsx:374-388),
+ * -M <= U for a constant U, so sdf(P) == A bit for bit wherever A > U and the march kernels skip the
+ * union loop there.  rmb_program_has_carve: 1 when the program was built with it (RMB_CARVE=0 in the
+ * environment builds without).  rmb_probe_carve: n points in, n*4 floats out: sdf(P) as the march
+ * kernels evaluate it, A(P), U, and sdf(P) as the guarded reference evaluation (rmb_probe's). */
+int rmb_program_has_carve(rmb_program* prog);
+rmb_status rmb_probe_carve(rmb_ctx* ctx, rmb_program* prog, const float* points_xyz, int n, float* out4);
 /* Lowering + NVRTC compile for sm_100a without touching a GPU (build checks, offline SASS
  * inspection).  cubin_out/source_out may be NULL. */
 rmb_status rmb_compile_only(const char* scene_glsl, size_t scene_len, int flavour, const rmb_spec_uniform* spec,
                             int n_spec, char* infolog, size_t infolog_cap, void* cubin_out, size_t cubin_cap,
                             size_t* cubin_bytes, char* source_out, size_t source_cap);
+/* The lowering alone (GLSL scene -> the CUDA C++ translation unit NVRTC would be given), no compile:
+ * scene-level diagnostics (missing sdf, unsupported uniform types; Validate.tsx:8-57 asks the GLSL
+ * compiler the same questions) in milliseconds, and the text the CPU tests inspect. */
+rmb_status rmb_translate_only(const char* scene_glsl, size_t scene_len, int flavour, const rmb_spec_uniform* spec,
+                              int n_spec, char* infolog, size_t infolog_cap, char* source_out, size_t source_cap);
 /* FP32 FMA throughput of this GPU in TFLOP/s (register-only FFMA kernel, best of `seconds` of
  * launches): the roofline denominator for this FP32-bound path. */
 rmb_status rmb_measure_fp32_peak(rmb_ctx* ctx, double seconds, double* tflops);

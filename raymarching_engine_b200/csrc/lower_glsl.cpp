@@ -16,6 +16,7 @@
 #include "lower_glsl.h"
 
 #include <cctype>
+#include <algorithm>
 #include <cstring>
 #include <map>
 
@@ -401,6 +402,358 @@ LowerResult lower_scene(const std::string& glsl, const std::set<std::string>& co
     }
     if (brace != 0) return fail(n ? T[n - 1].line : 1, "unexpected end of source: unbalanced '{'");
 
+
+    // ---- pass 1b: "carve" analysis --------------------------------------------------------------
+    // Recognises   float sdf(vec3 P) { float M = <literal>; ... M = min(length(..) - K, M); ...
+    //                                  [V =] max(A, -M); return .. }
+    // i.e. a union of shapes M carved out of an outer shape A (max(A, -M), the CSG difference).  When every
+    // term of the union is `length(..) - K` with K independent of the position, -M can never exceed
+    // U = max(-<literal>, max K) whatever the position is (length() >= 0 and rounding is monotonic; NaN
+    // terms are dropped by min), so wherever A > U the function returns A bit for bit.  The march
+    // kernels use that for the far field (raymarch_kernel.cuh, RM_HAS_CARVE): A costs ~10 instructions,
+    // the union loop hundreds.  Two helper functions are emitted after the scene: rm_carve_outer(P) = A
+    // and rm_carve_bound() = U, the latter being the scene's own sdf body with each accepted length()
+    // replaced by zero and the final max() by (-M), so that U is computed by the same arithmetic, from
+    // the same uniforms, as the terms it bounds.  Anything the analysis does not fully understand
+    // (branches, early returns, macros, shadowing, a K that mentions position-dependent values, ...)
+    // leaves the scene without the helpers.
+    struct Carve {
+        bool ok = false;
+        size_t body_open = 0, body_close = 0;       // '{' and '}' of sdf
+        std::string param, m_name;
+        size_t ea_first = 0, ea_last = 0;           // token range of A
+        size_t max_first = 0, max_close = 0;        // `max` .. its ')'
+        std::vector<size_t> len_tokens;             // the accepted `length` identifiers
+    } carve;
+    if (R.pure) {
+        auto live = [&](size_t k) { return k < n && !T[k].drop && T[k].kind != kPP; };
+        auto next_live = [&](size_t k) { k++; while (k < n && !live(k)) k++; return k; };
+        auto prev_live = [&](size_t k) -> size_t { while (k > 0) { k--; if (live(k)) return k; } return n; };
+        auto match_close = [&](size_t open) -> size_t {
+            int d = 0;
+            for (size_t k = open; k < n; k++) {
+                if (!live(k)) continue;
+                const std::string& w = T[k].text;
+                if (w == "(" || w == "[" || w == "{") d++;
+                else if (w == ")" || w == "]" || w == "}") { d--; if (d == 0) return k; }
+            }
+            return n;
+        };
+        auto is_for = [&](size_t k) { const std::string& w = T[k].text; return T[k].kind == kIdent && w.size() >= 3 && w.compare(w.size() - 3, 3, "for") == 0 && (w.size() == 3 || w[w.size() - 4] == ' '); };
+        static const std::set<std::string> assign_ops = {"=", "+=", "-=", "*=", "/=", "%=", "&=", "|=", "^=", "<<=", ">>=", "++", "--"};
+        static const std::set<std::string> banned = {"if", "else", "while", "do", "switch", "case", "default", "break", "continue", "discard", "goto", "struct"};
+        static const std::set<std::string> pure_builtins = {
+            "pow", "exp", "exp2", "log", "log2", "sqrt", "inversesqrt", "abs", "sign", "floor", "ceil", "fract", "mod", "min", "max",
+            "clamp", "mix", "step", "smoothstep", "sin", "cos", "tan", "asin", "acos", "atan", "radians", "degrees", "length",
+            "distance", "dot", "cross", "normalize", "round", "trunc"};
+        char bt; int bc;
+        std::set<std::string> uniform_names;
+        for (const UniformDecl& u : R.uniforms) uniform_names.insert(u.name);
+        bool has_pp = false, has_ref_params = false;
+        for (size_t k = 0; k < n; k++) {
+            if (T[k].kind == kPP && !T[k].drop) has_pp = true;
+            if (live(k) && T[k].kind == kIdent && !T[k].text.empty() && T[k].text.back() == '&') has_ref_params = true;
+        }
+        // locate `float sdf ( [const] vec3 P ) {` at global scope (exactly one definition)
+        size_t fn = n; int defs = 0;
+        {
+            int depth = 0;
+            for (size_t k = 0; k < n; k++) {
+                if (!live(k)) continue;
+                if (T[k].text == "{") depth++;
+                else if (T[k].text == "}") depth--;
+                else if (depth == 0 && T[k].kind == kIdent && T[k].text == "sdf") {
+                    size_t o = next_live(k);
+                    if (o < n && T[o].text == "(") { defs++; fn = k; }
+                }
+            }
+        }
+        do {
+            if (has_pp || has_ref_params || defs != 1) break;
+            size_t ty = prev_live(fn);
+            if (ty == n || T[ty].text != "float") break;
+            size_t o = next_live(fn), q = next_live(o);
+            if (q < n && T[q].text == "const") q = next_live(q);
+            if (q >= n || T[q].text != "vec3") break;
+            size_t pn = next_live(q);
+            if (pn >= n || T[pn].kind != kIdent) break;
+            size_t cp = next_live(pn);
+            if (cp >= n || T[cp].text != ")") break;
+            size_t ob = next_live(cp);
+            if (ob >= n || T[ob].text != "{") break;
+            size_t cb = match_close(ob);
+            if (cb == n) break;
+            carve.param = T[pn].text;
+            carve.body_open = ob; carve.body_close = cb;
+
+            // ---- declarations, control flow, assignments
+            struct Local { size_t decl = 0; std::string type; size_t init_first = 0, init_last = 0; bool has_init = false; int depth = 0; bool counter = false; bool assigned = false; };
+            std::map<std::string, Local> locals;
+            std::vector<std::pair<size_t, size_t> > for_headers;   // '(' and ')' of each loop header
+            bool bad = false;
+            int returns = 0; size_t ret_tok = n;
+            {
+                int depth = 1;
+                for (size_t k = next_live(ob); k < cb && !bad; k = next_live(k)) {
+                    const std::string& w = T[k].text;
+                    if (w == "{") { depth++; continue; }
+                    if (w == "}") { depth--; continue; }
+                    if (w == "?") { bad = true; break; }
+                    if (T[k].kind != kIdent) continue;
+                    { size_t pv = prev_live(k); if (pv != n && T[pv].text == ".") continue; }   // field / swizzle
+                    if (banned.count(w)) { bad = true; break; }
+                    if (w == "return") { returns++; ret_tok = k; if (depth != 1) bad = true; continue; }
+                    if (is_for(k)) {
+                        size_t ho = next_live(k);
+                        if (ho >= cb || T[ho].text != "(") { bad = true; break; }
+                        size_t hc = match_close(ho);
+                        if (hc == n || hc >= cb) { bad = true; break; }
+                        for_headers.push_back({ho, hc});
+                        continue;
+                    }
+                    if (uniform_type_info(w, &bt, &bc)) {
+                        size_t nx = next_live(k);
+                        if (nx >= cb || T[nx].kind != kIdent) continue;           // constructor call etc.
+                        // declaration: TYPE NAME [= init] ;   (one declarator, no arrays)
+                        Local L;
+                        L.decl = nx; L.type = w; L.depth = depth;
+                        const std::string name = T[nx].text;
+                        if (locals.count(name) || name == carve.param || uniform_names.count(name)) { bad = true; break; }
+                        size_t a = next_live(nx);
+                        if (a >= cb) { bad = true; break; }
+                        if (T[a].text == "=") {
+                            L.has_init = true;
+                            L.init_first = next_live(a);
+                            int d = 0; size_t e = L.init_first;
+                            for (; e < cb; e = next_live(e)) {
+                                const std::string& x = T[e].text;
+                                if (x == "(" || x == "[") d++;
+                                else if (x == ")" || x == "]") d--;
+                                else if (d == 0 && x == ",") { bad = true; break; }
+                                else if (d == 0 && x == ";") break;
+                                if (d < 0) { bad = true; break; }
+                            }
+                            if (bad || e >= cb || e == L.init_first) { bad = true; break; }
+                            L.init_last = prev_live(e);
+                        } else if (T[a].text != ";") { bad = true; break; }
+                        locals[name] = L;
+                        k = nx;
+                        continue;
+                    }
+                }
+            }
+            if (bad || returns != 1) break;
+            // writes to locals / the parameter other than the declaration itself
+            std::map<std::string, std::vector<size_t> > writes;
+            for (size_t k = next_live(ob); k < cb; k = next_live(k)) {
+                if (T[k].kind != kIdent) continue;
+                { size_t pv = prev_live(k); if (pv != n && T[pv].text == ".") continue; }
+                const std::string& w = T[k].text;
+                const bool is_local = locals.count(w) != 0;
+                if (!is_local && w != carve.param) continue;
+                if (is_local && locals[w].decl == k) continue;
+                size_t e = k, nx = next_live(k);
+                while (nx < cb && (T[nx].text == "." || T[nx].text == "[")) {
+                    if (T[nx].text == ".") { e = next_live(nx); } else { e = match_close(nx); if (e == n) { bad = true; break; } }
+                    nx = next_live(e);
+                }
+                if (bad) break;
+                size_t pv = prev_live(k);
+                if ((nx < cb && assign_ops.count(T[nx].text)) || (pv != n && (T[pv].text == "++" || T[pv].text == "--"))) writes[w].push_back(k);
+            }
+            if (bad || writes.count(carve.param)) break;
+            // loop headers: only type names, the loop's own counter, uniforms and literals
+            for (auto& h : for_headers) {
+                std::string counter;
+                for (size_t k = next_live(h.first); k < h.second && !bad; k = next_live(k)) {
+                    if (T[k].kind != kIdent) continue;
+                    const std::string& w = T[k].text;
+                    if (uniform_type_info(w, &bt, &bc) || w == "const") continue;
+                    auto L = locals.find(w);
+                    if (L != locals.end() && L->second.decl > h.first && L->second.decl < h.second) {
+                        if (!counter.empty() && counter != w) bad = true;
+                        counter = w;
+                        continue;
+                    }
+                    if (uniform_names.count(w)) continue;
+                    bad = true;
+                }
+                if (bad || counter.empty()) { bad = true; break; }
+                for (size_t wtok : writes[counter]) if (!(wtok > h.first && wtok < h.second)) bad = true;
+                locals[counter].counter = true;
+            }
+            if (bad) break;
+            // position-independent locals, in declaration order
+            std::set<std::string> clean;
+            for (auto& kv : locals) if (kv.second.counter) clean.insert(kv.first);
+            auto idents_clean = [&](size_t first, size_t last) {
+                for (size_t k = first; k <= last && k < n; k = next_live(k)) {
+                    if (T[k].kind != kIdent) continue;
+                    size_t pv = prev_live(k);
+                    if (pv != n && T[pv].text == ".") continue;
+                    const std::string& w = T[k].text;
+                    if (uniform_type_info(w, &bt, &bc)) continue;
+                    size_t nx = next_live(k);
+                    const bool call = nx < n && T[nx].text == "(";
+                    if (call) { if (pure_builtins.count(w)) continue; return false; }
+                    if (clean.count(w) || uniform_names.count(w)) continue;
+                    return false;
+                }
+                return true;
+            };
+            {
+                std::vector<std::pair<size_t, std::string> > order;
+                for (auto& kv : locals) order.push_back({kv.second.decl, kv.first});
+                std::sort(order.begin(), order.end());
+                for (auto& o2 : order) {
+                    Local& L = locals[o2.second];
+                    if (L.counter || !L.has_init || writes.count(o2.second)) continue;
+                    if (idents_clean(L.init_first, L.init_last)) clean.insert(o2.second);
+                }
+            }
+            // `length ( ... ) - K` with K a product/quotient of position-independent primaries
+            auto accept_len = [&](size_t first, size_t last) -> size_t {     // returns the `length` token or n
+                if (T[first].kind != kIdent || T[first].text != "length") return n;
+                size_t o2 = next_live(first);
+                if (o2 > last || T[o2].text != "(") return n;
+                size_t c2 = match_close(o2);
+                if (c2 == n || c2 >= last) return n;
+                size_t minus = next_live(c2);
+                if (minus >= last + 1 || T[minus].text != "-") return n;
+                size_t kf = next_live(minus);
+                if (kf > last) return n;
+                int d = 0;
+                for (size_t k = kf; k <= last; k = next_live(k)) {
+                    const std::string& x = T[k].text;
+                    if (x == "(" || x == "[") d++;
+                    else if (x == ")" || x == "]") d--;
+                    else if (d == 0 && T[k].kind == kPunct && x != "*" && x != "/" && x != ".") return n;
+                    if (d < 0) return n;
+                }
+                if (d != 0 || !idents_clean(kf, last)) return n;
+                return first;
+            };
+            // ---- the return statement
+            size_t semi_end = prev_live(cb);
+            if (semi_end == n || T[semi_end].text != ";") break;
+            size_t rx = next_live(ret_tok);
+            size_t max_tok = n, stmt_semi = semi_end;
+            std::string assigned_to;
+            if (rx < cb && T[rx].text == "max") {
+                max_tok = rx;
+            } else if (rx < cb && T[rx].kind == kIdent && next_live(rx) == semi_end) {
+                // V = max(..); return V;
+                assigned_to = T[rx].text;
+                size_t ps = prev_live(ret_tok);
+                if (ps == n || T[ps].text != ";") break;
+                stmt_semi = ps;
+                // walk back to the start of that statement
+                size_t st = ps; int d = 0; bool found = false;
+                while (true) {
+                    size_t pv = prev_live(st);
+                    if (pv == n || pv <= ob) { found = (pv == ob); break; }
+                    const std::string& x = T[pv].text;
+                    if (x == ")" || x == "]") d++;
+                    else if (x == "(" || x == "[") d--;
+                    else if (d == 0 && (x == ";" || x == "{" || x == "}")) { found = true; break; }
+                    st = pv;
+                }
+                if (!found) break;
+                size_t a = st;
+                if (T[a].text == "float") a = next_live(a);
+                if (T[a].text != assigned_to) break;
+                size_t eq = next_live(a);
+                if (T[eq].text != "=") break;
+                max_tok = next_live(eq);
+                if (max_tok >= cb || T[max_tok].text != "max") break;
+                // that statement must sit at the function's top level
+                int depth = 1; bool top = true;
+                for (size_t k = next_live(ob); k < st; k = next_live(k)) { if (T[k].text == "{") depth++; else if (T[k].text == "}") depth--; }
+                top = depth == 1;
+                if (!top) break;
+            } else break;
+            size_t mo = next_live(max_tok);
+            if (mo >= cb || T[mo].text != "(") break;
+            size_t mc = match_close(mo);
+            if (mc == n || next_live(mc) != stmt_semi) break;
+            if (assigned_to.empty() && stmt_semi != semi_end) break;
+            size_t comma = n; int commas = 0;
+            { int d = 0; for (size_t k = next_live(mo); k < mc; k = next_live(k)) { const std::string& x = T[k].text; if (x == "(" || x == "[") d++; else if (x == ")" || x == "]") d--; else if (d == 0 && x == ",") { commas++; comma = k; } } }
+            if (commas != 1) break;
+            size_t a1f = next_live(mo), a1l = prev_live(comma), a2f = next_live(comma), a2l = prev_live(mc);
+            auto neg_ident = [&](size_t f, size_t l) -> std::string { return (T[f].text == "-" && next_live(f) == l && T[l].kind == kIdent) ? T[l].text : std::string(); };
+            std::string m = neg_ident(a2f, a2l);
+            size_t eaf = a1f, eal = a1l;
+            if (m.empty() || !locals.count(m)) { m = neg_ident(a1f, a1l); eaf = a2f; eal = a2l; }
+            if (m.empty() || !locals.count(m)) break;
+            Local& ML = locals[m];
+            if (ML.type != "float" || ML.depth != 1 || !ML.has_init) break;
+            {   // initialiser: [+-] literal
+                size_t v = ML.init_first;
+                if (T[v].text == "-" || T[v].text == "+") v = next_live(v);
+                if (v != ML.init_last || T[v].kind != kNumber) break;
+            }
+            // A: the parameter, uniforms, literals and pure built-ins only
+            {
+                std::set<std::string> saved = clean;
+                clean.clear();
+                clean.insert(carve.param);
+                const bool ok = idents_clean(eaf, eal);
+                clean = saved;
+                if (!ok) break;
+            }
+            // ---- every other mention of M: `M = min(X, M);` / `M = min(M, X);`
+            std::set<size_t> accounted;
+            accounted.insert(ML.decl);
+            for (size_t k = next_live(mo); k < mc; k = next_live(k)) if (T[k].kind == kIdent && T[k].text == m) accounted.insert(k);
+            if (assigned_to == m) { accounted.insert(prev_live(prev_live(max_tok))); accounted.insert(rx); }
+            for (size_t k = next_live(ob); k < cb && !bad; k = next_live(k)) {
+                if (T[k].kind != kIdent || T[k].text != m || accounted.count(k)) continue;
+                size_t pv = prev_live(k);
+                if (pv == n || !(T[pv].text == ";" || T[pv].text == "{" || T[pv].text == "}" || T[pv].text == ")")) { bad = true; break; }
+                if (T[pv].text == ")") {
+                    // only as the un-braced body of a loop:  for (...) M = min(..);
+                    bool hdr = false;
+                    for (auto& h : for_headers) if (h.second == pv) hdr = true;
+                    if (!hdr) { bad = true; break; }
+                }
+                size_t eq = next_live(k), mn = next_live(eq), o2 = next_live(mn);
+                if (o2 >= cb || T[eq].text != "=" || T[mn].text != "min" || T[o2].text != "(") { bad = true; break; }
+                size_t c2 = match_close(o2);
+                if (c2 == n || c2 >= cb || T[next_live(c2)].text != ";") { bad = true; break; }
+                size_t cm = n; int cms = 0;
+                { int d = 0; for (size_t q2 = next_live(o2); q2 < c2; q2 = next_live(q2)) { const std::string& x = T[q2].text; if (x == "(" || x == "[") d++; else if (x == ")" || x == "]") d--; else if (d == 0 && x == ",") { cms++; cm = q2; } } }
+                if (cms != 1) { bad = true; break; }
+                size_t x1f = next_live(o2), x1l = prev_live(cm), x2f = next_live(cm), x2l = prev_live(c2);
+                size_t xf, xl, mtok;
+                if (x2f == x2l && T[x2f].text == m) { xf = x1f; xl = x1l; mtok = x2f; }
+                else if (x1f == x1l && T[x1f].text == m) { xf = x2f; xl = x2l; mtok = x1f; }
+                else { bad = true; break; }
+                for (size_t q2 = xf; q2 <= xl; q2 = next_live(q2)) if (T[q2].kind == kIdent && T[q2].text == m) bad = true;
+                if (bad) break;
+                size_t len_tok = n;
+                if (xf == xl && T[xf].kind == kIdent && locals.count(T[xf].text)) {
+                    Local& X = locals[T[xf].text];
+                    if (X.type == "float" && X.has_init && !writes.count(T[xf].text) && !X.counter) len_tok = accept_len(X.init_first, X.init_last);
+                } else len_tok = accept_len(xf, xl);
+                if (len_tok == n) { bad = true; break; }
+                carve.len_tokens.push_back(len_tok);
+                accounted.insert(k);
+                accounted.insert(mtok);
+            }
+            if (bad) break;
+            if (writes.count(m)) {
+                // every write to M is one of the accepted statements (or the final assignment)
+                for (size_t wtok : writes[m]) if (!accounted.count(wtok)) bad = true;
+            }
+            if (bad) break;
+            carve.ok = true;
+            carve.m_name = m;
+            carve.ea_first = eaf; carve.ea_last = eal;
+            carve.max_first = max_tok; carve.max_close = mc;
+        } while (false);
+    }
+
     // ---- pass 2: domain-repetition idiom -----------------------------------------------------
     // `mod(X + H1, S) - H2` -> rm_rep(X, H1, S, H2) and `mod(X, S) - H2` -> rm_rep0(X, S, H2), where the
     // whole pattern is one operand of nothing tighter than the binary minus.  glsl_rt.h defines both
@@ -616,6 +969,23 @@ LowerResult lower_scene(const std::string& glsl, const std::set<std::string>& co
         }
         pk += trailing;
         R.body_packed = pk;
+    }
+
+    if (carve.ok) {
+        // helper functions (members of the fragment struct, after the scene): token texts as they stand
+        // after pass 2, so the domain-repetition rewrite applies to them exactly as it does to sdf()
+        auto live = [&](size_t k) { return k < n && !T[k].drop && T[k].kind != kPP; };
+        std::string outer, bound;
+        for (size_t k = carve.ea_first; k <= carve.ea_last; k++) if (live(k)) { outer += ' '; outer += T[k].text; }
+        std::set<size_t> lens(carve.len_tokens.begin(), carve.len_tokens.end());
+        for (size_t k = carve.body_open + 1; k < carve.body_close; k++) {
+            if (!live(k)) continue;
+            bound += ' ';
+            if (k == carve.max_first) { bound += "(-" + carve.m_name + ")"; k = carve.max_close; continue; }
+            bound += lens.count(k) ? std::string("rm_len0") : T[k].text;
+        }
+        R.carve_text = "\nfloat rm_carve_outer(vec3 " + carve.param + ") { return" + outer + "; }\n" +
+                       "float rm_carve_bound() { vec3 " + carve.param + " = vec3(0.0f);" + bound + " }\n";
     }
     R.ok = true;
     return R;

@@ -28,6 +28,10 @@ struct LowerResult {
     std::vector<UniformDecl> uniforms;  // scene-declared uniforms, removed from `body`
     std::set<std::string> functions;    // functions DEFINED at global scope
     bool pure = true;                   // no mutable per-invocation state reachable from scene code
+    std::string carve_text;             // non-empty when sdf() is a union of `length(..) - K` shapes carved out
+                                        // of an outer shape (max(A, -M)): definitions of rm_carve_outer(P) = A
+                                        // and rm_carve_bound() = an upper bound of -M valid at every position,
+                                        // so that sdf(P) == A bit for bit wherever A > bound (lower_glsl.cpp 1b)
 };
 
 // `constant_names`: uniforms that will be compile-time constants in this program variant (baked).

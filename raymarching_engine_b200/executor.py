@@ -44,6 +44,10 @@ class Program:
         """True when the program marches two rays per lane with packed FP32 (glsl_pk.h)"""
         return bool(L.rmb_program_is_dual(self.handle))
 
+    def has_carve(self) -> bool:
+        """True when the march kernels take the far-field shortcut of a carved scene (include/rmb.h)"""
+        return bool(L.rmb_program_has_carve(self.handle))
+
     def dual_log(self) -> str:
         return (L.rmb_program_dual_log(self.handle) or b"").decode()
 
@@ -152,6 +156,20 @@ class RenderJobContext:                  # RenderJobExecutor.tsx:32-54
         out = (C.c_uint64 * 2)()
         L.rmb_counters_read(self.handle, out, 1 if reset else 0)
         return int(out[0]), int(out[1])
+
+    def counters3(self, reset: bool = False):
+        """(SDF evaluations, pixel-samples, evaluations that took the far-field shortcut)"""
+        out = (C.c_uint64 * 3)()
+        L.rmb_counters_read3(self.handle, out, 1 if reset else 0)
+        return int(out[0]), int(out[1]), int(out[2])
+
+    def probe_carve(self, program, points) -> np.ndarray:
+        """n x 4: sdf as the march kernels evaluate it, outer shape A, bound U, guarded sdf (rmb_probe_carve)"""
+        pts = np.ascontiguousarray(points, dtype=np.float32).reshape(-1, 3)
+        out = np.zeros((len(pts), 4), np.float32)
+        if L.rmb_probe_carve(self.handle, program.handle, pts.ctypes.data_as(C.c_void_p), len(pts), out.ctypes.data_as(C.c_void_p)) != 0:
+            raise RuntimeError(self.last_error())
+        return out
 
     def _pinned(self, key, shape, dtype) -> np.ndarray:
         """numpy view of a cached pinned host buffer (rmb_host_alloc) for readbacks"""

@@ -1,0 +1,256 @@
+"""Far-field shortcut for carved scenes (lower_glsl.cpp pass 1b, include/rmb.h rmb_program_has_carve).
+
+The product has no CPU path, so the claim "sdf(P) == A(P) bit for bit wherever A(P) > U" is checked here
+on the LOWERED TEXT itself: the scene functions and the two helpers the lowering emits are cut out of the
+translation unit rmb_compile_only returns, compiled with g++ against the shared deterministic math
+(glsl_rt.h, exact policy, the oracle's flags) and evaluated at a few hundred thousand positions, including
+the non-finite ones escaping rays reach.  The GPU side of the same claim is tests/test_parity_gpu.py
+(test_carve_*: probe kernel, far-field on/off frames, oracle parity of every scene with the shortcut on).
+"""
+import ctypes as C
+import os
+import re
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import raymarching_engine_b200 as rm
+from raymarching_engine_b200 import _lib
+from conftest import scene_source
+
+L = _lib.lib
+ROOT = Path(__file__).resolve().parent.parent
+DEVICE_SRC = ROOT / "raymarching_engine_b200" / "csrc" / "device_src"
+
+
+def translation_unit(src, spec=None, flavour=_lib.FLAVOUR_EXACT, compile=False):
+    log = C.create_string_buffer(1 << 16)
+    n = C.c_size_t(0)
+    out = C.create_string_buffer(2 << 20)
+    arr, ns = _lib.make_spec_array(spec)
+    b = src.encode()
+    if compile:       # through NVRTC for sm_100a as well
+        st = L.rmb_compile_only(b, len(b), flavour, arr, ns, log, len(log), None, 0, C.byref(n), out, len(out))
+    else:
+        st = L.rmb_translate_only(b, len(b), flavour, arr, ns, log, len(log), out, len(out))
+    assert st == _lib.RMB_OK, log.value.decode()
+    return out.value.decode()
+
+
+def has_carve(src, spec=None, compile=False):
+    tu = translation_unit(src, spec, compile=compile)
+    on = "#define RM_HAS_CARVE 1" in tu
+    assert on == ("float rm_carve_outer(" in tu) == ("float rm_carve_bound(" in tu)
+    return on
+
+
+SDF = """
+uniform float R;
+uniform float s0;
+float sdf(vec3 p) {
+  float m = 1000.0;
+  for (float i = 0.0; i < 4.0; i++) {
+    float sf = pow(s0, i);
+    vec3 d = mod(p + vec3(0.5 * sf), sf) - vec3(sf / 2.0);
+    %s
+  }
+  %s
+}
+"""
+
+
+def _scene(loop_tail="float dist = length(d) - 0.3 * sf; m = min(dist, m);", end="return max(length(p) - R, -m);"):
+    return SDF % (loop_tail, end)
+
+
+def test_accepted_shapes():
+    assert has_carve(scene_source("guide"))
+    assert has_carve(scene_source("guide"), rm.default_custom_settings(scene_source("guide")))
+    assert has_carve(scene_source("inline-default"))
+    assert has_carve(scene_source("fractal1"))
+    assert has_carve(_scene())
+    assert has_carve(_scene("m = min(m, length(d) - 0.3 * sf);"))                       # inline term, M first
+    assert has_carve(_scene(end="m = max(-m, length(p) - R); return m;"), compile=True)  # operands swapped, assigned; NVRTC takes it
+    assert has_carve(_scene(end="float r = max(length(p) - R, -m); return r;"))
+    assert has_carve(_scene("float k = 0.3 * sf / 2.0; float dist = length(d) - k; m = min(dist, m);"))
+    for name in ("sphere-grid", "mandelbulb", "menger-sponge", "tree", "smooth-tree", "rotation-fractal"):
+        assert not has_carve(scene_source(name)), name                                    # not of that form
+
+
+@pytest.mark.parametrize("loop_tail,end", [
+    # a term whose offset depends on the position
+    ("float dist = length(d) - 0.3 * sf * p.x; m = min(dist, m);", None),
+    ("float k = d.x; float dist = length(d) - k; m = min(dist, m);", None),
+    # not `length - K`
+    ("float dist = length(d) * 0.5 - 0.3 * sf; m = min(dist, m);", None),
+    ("float dist = length(d) - 0.3 * sf + p.y; m = min(dist, m);", None),
+    ("float dist = -length(d) - 0.3 * sf; m = min(dist, m);", None),
+    ("float dist = d.x - 0.3 * sf; m = min(dist, m);", None),
+    ("float dist = length(d) - 0.3 * sf; m = max(dist, m);", None),
+    # control flow the analysis does not follow
+    ("float dist = length(d) - 0.3 * sf; if (p.x > 0.0) m = min(dist, m);", None),
+    ("float dist = length(d) - 0.3 * sf; m = p.x > 0.0 ? min(dist, m) : m;", None),
+    ("float dist = length(d) - 0.3 * sf; m = min(dist, m); if (m < 0.0) break;", None),
+    ("float dist = length(d) - 0.3 * sf; m = min(dist, m); if (m < 0.0) return m;", None),
+    # the accumulator or the term is touched some other way
+    ("float dist = length(d) - 0.3 * sf; m = min(dist, m); m -= 0.1;", None),
+    ("float dist = length(d) - 0.3 * sf; dist -= p.x; m = min(dist, m);", None),
+    ("float dist = length(d) - 0.3 * sf; m = min(dist, m) - 0.1;", None),
+    ("float dist = length(d) - 0.3 * sf; float q = m; m = min(dist, m);", None),
+    ("sf = sf * p.x; float dist = length(d) - 0.3 * sf; m = min(dist, m);", None),
+    ("i += p.x; float dist = length(d) - 0.3 * sf; m = min(dist, m);", None),
+    ("p = p * 2.0; float dist = length(d) - 0.3 * sf; m = min(dist, m);", None),
+    # the result is not max(A, -M), or A is not a function of the position and uniforms alone
+    (None, "return max(length(p) - R, m);"),
+    (None, "return max(length(p) - R, -m) + 0.1;"),
+    (None, "return min(length(p) - R, -m);"),
+    (None, "return max(length(p) - R, -m * 2.0);"),
+    (None, "float t = m * 0.5; return max(length(p) - t, -m);"),
+    (None, "return max(length(p) - R, max(-m, 0.0));"),
+])
+def test_rejected_shapes(loop_tail, end):
+    kw = {}
+    if loop_tail is not None:
+        kw["loop_tail"] = loop_tail
+    if end is not None:
+        kw["end"] = end
+    assert not has_carve(_scene(**kw))
+
+
+def test_rejected_contexts():
+    good = _scene()
+    assert has_carve(good)
+    assert not has_carve("#define OFF 0.3\n" + good)                                          # macros can hide anything
+    assert not has_carve(good.replace("float m = 1000.0;", "float m = R;"))                 # not a literal
+    assert not has_carve(good.replace("float sdf(vec3 p) {", "float sdf(vec3 p) {\n  p = p.zyx;"))
+    assert not has_carve(good + "\nvoid twist(inout vec3 q) { q = q.zyx; }\n")              # reference parameters anywhere
+    assert not has_carve(good.replace("for (float i = 0.0; i < 4.0; i++)", "for (float i = 0.0; i < p.x; i++)"))
+    assert not has_carve(good.replace("float sf = pow(s0, i);", "float sf = pow(s0, i); float R = 1.0;"))   # shadows a uniform
+    assert not has_carve("float seedy = 0.0;\n" + good)                                       # impure scene: no wavefront pipeline at all
+    # the switch
+    os.environ["RMB_CARVE"] = "0"
+    try:
+        assert not has_carve(good)
+    finally:
+        del os.environ["RMB_CARVE"]
+
+
+HARNESS = r"""
+#include <cstdio>
+#include <cstdlib>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+#define GLSL_NS xg
+#define GLSL_FAST 0
+#include "glsl_rt.h"
+namespace xg {
+%(uniforms)s
+struct Frag {
+    vec2 texcoord;
+    ivec2 rm_texSize;
+    template <class V> static float rm_len0(const V&) { return 0.0f; }
+    float sdfSphere(vec3 position, vec3 center, float radius) { return distance(position, center) - radius; }
+%(scene)s
+};
+}
+int main(int argc, char** argv) {
+    // stdin: n, then n * 3 floats; stdout: n * 3 floats (sdf, A, U), all binary
+    uint32_t n = 0;
+    if (fread(&n, 4, 1, stdin) != 1) return 2;
+    std::vector<float> in(3 * (size_t)n), out(3 * (size_t)n);
+    if (fread(in.data(), 4, in.size(), stdin) != in.size()) return 2;
+    xg::Frag f;
+    f.texcoord = xg::vec2(0.5f, 0.5f);
+    f.rm_texSize = xg::ivec2(1, 1);
+    const float U = f.rm_carve_bound();
+    for (uint32_t i = 0; i < n; i++) {
+        const xg::vec3 p(in[3 * i], in[3 * i + 1], in[3 * i + 2]);
+        out[3 * i] = f.sdf(p);
+        out[3 * i + 1] = f.rm_carve_outer(p);
+        out[3 * i + 2] = U;
+    }
+    fwrite(out.data(), 4, out.size(), stdout);
+    return 0;
+}
+"""
+
+
+def _cxx_value(v):
+    a = np.atleast_1d(np.asarray(v, dtype=np.float32))
+    lit = ["%sf" % np.format_float_scientific(x, unique=True) for x in a]
+    return lit[0] if len(lit) == 1 else "vec%d(%s)" % (len(lit), ", ".join(lit))
+
+
+def _build_harness(tmp_path, src, values):
+    tu = translation_unit(src)                                    # generic variant: every scene uniform dynamic
+    m = re.search(r'#line 1 "scene.glsl"\n(.*?)\n#line \d+ "raymarch_kernel.cuh"', tu, re.S)
+    assert m
+    scene = m.group(1)
+    assert "rm_carve_outer" in scene and "rm_len0" in scene
+    decls = re.findall(r"^__constant__ (\w+) (\w+);$", tu, re.M)
+    uniforms = "".join("static %s %s = %s;\n" % (t, nme, _cxx_value(values[nme])) for t, nme in decls if nme in values)
+    assert len(uniforms.splitlines()) == len(values)
+    cpp = tmp_path / "carve_harness.cpp"
+    cpp.write_text(HARNESS % {"uniforms": uniforms, "scene": scene})
+    exe = tmp_path / "carve_harness"
+    subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-mfma", "-Wno-unknown-pragmas", "-I", str(DEVICE_SRC),
+                    str(cpp), "-o", str(exe)], check=True)
+    return exe
+
+
+def _points(rng, centre, radius):
+    c = np.asarray(centre, np.float32)
+    near = c + rng.uniform(-1.3, 1.3, (120000, 3)).astype(np.float32) * np.float32(radius)
+    shell = c + (rng.normal(size=(60000, 3)) * 1.0).astype(np.float32)
+    shell = c + (shell - c) / np.linalg.norm(shell - c, axis=1, keepdims=True).astype(np.float32) * \
+        (np.float32(radius) + rng.uniform(-0.1, 1.5, (60000, 1)).astype(np.float32))
+    with np.errstate(over="ignore"):        # overflow to +-inf is wanted
+        far = (rng.normal(size=(60000, 3)) * 10.0 ** rng.uniform(0, 38.5, (60000, 1))).astype(np.float32)
+    tiny = (rng.normal(size=(2000, 3)) * 10.0 ** rng.uniform(-45, -30, (2000, 1))).astype(np.float32)
+    special = np.array([[np.inf, 0, 0], [0, -np.inf, 1], [np.inf, np.inf, -np.inf], [np.nan, 1, 2], [1, np.nan, np.inf],
+                        [3.4e38, 3.4e38, 3.4e38], [-3.4e38, 1, 1], [0, 0, 0], [-0.0, -0.0, -0.0], [1e19, 1e19, 1e19], [2e19, 0, 0]], np.float32)
+    with np.errstate(all="ignore"):
+        return np.ascontiguousarray(np.concatenate([near, shell, far, tiny, special]).astype(np.float32))
+
+
+def _run(exe, pts):
+    blob = np.uint32(len(pts)).tobytes() + pts.tobytes()
+    r = subprocess.run([str(exe)], input=blob, stdout=subprocess.PIPE, check=True)
+    return np.frombuffer(r.stdout, np.float32).reshape(-1, 3)
+
+
+@pytest.mark.parametrize("case", ["guide-defaults", "guide-varied", "inline-default"])
+def test_far_field_value_is_the_outer_shape_bit_for_bit(tmp_path, case):
+    rng = np.random.default_rng(20261017)
+    if case == "inline-default":
+        src, values, centre, radius = scene_source("inline-default"), {}, (0, 0, 0), 5.0
+        expect_U = np.float32(0.21) * np.float32(3.0)
+    else:
+        src = scene_source("guide")
+        values = {k: (v.data[0] if v.count == 1 else tuple(v.data)) for k, v in rm.default_custom_settings(src).items()}
+        values = {k: v for k, v in values.items() if k in ("bigSphereSize", "fractalIterations", "gridScaleFactor", "bigSphereCenter", "fractalColor")}
+        expect_U = np.float32(0.21) * np.float32(3.0)
+        if case == "guide-varied":
+            values.update(bigSphereSize=2.37, fractalIterations=5.0, gridScaleFactor=0.41, bigSphereCenter=(1.5, -0.25, 3.0))
+            expect_U = None
+        centre, radius = values["bigSphereCenter"], values["bigSphereSize"]
+    exe = _build_harness(tmp_path, src, values)
+    pts = _points(rng, centre, radius)
+    out = _run(exe, pts)
+    sdf, A, U = out[:, 0], out[:, 1], out[:, 2]
+    assert np.all(U == U[0]) and np.isfinite(U[0])
+    if expect_U is not None:
+        assert U[0] == expect_U                                   # 0.21 * sf of the coarsest grid (sf = 1/gridScaleFactor)
+    with np.errstate(invalid="ignore"):
+        far = A > U[0]
+    # the claim
+    np.testing.assert_array_equal(sdf[far].view(np.uint32), A[far].view(np.uint32))
+    # and it is not vacuous: both sides of the bound are well populated, the near side really differs
+    assert far.sum() > 50000 and (~far).sum() > 50000
+    near_differs = (sdf[~far].view(np.uint32) != A[~far].view(np.uint32)).mean()
+    assert near_differs > 0.2
+    # non-finite positions included
+    assert np.isinf(A[far]).any()

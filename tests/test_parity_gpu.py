@@ -581,6 +581,7 @@ def test_two_rays_per_lane_march_is_bit_identical(ctx, name, dual_expected, monk
     src = scene_source(name)
     custom = rm.default_custom_settings(src)
     outs = []
+    monkeypatch.setenv("RMB_CARVE", "0")                # the far-field pipeline of carved scenes uses the one-ray kernels
     for dual in ("0", "1"):
         monkeypatch.setenv("RMB_DUAL", dual)
         c = rm.load_render_job_context(device=0)      # programs are cached per context: fresh context per setting
@@ -606,3 +607,85 @@ def test_two_rays_per_lane_march_is_bit_identical(ctx, name, dual_expected, monk
         np.testing.assert_array_equal(_canon(a[1]), _canon(b[1]))
         np.testing.assert_array_equal(a[2], b[2])
         assert a[3] == b[3]                             # same number of SDF evaluations and pixel-samples
+
+
+def _carve_points(rng, centre, radius):
+    c = np.asarray(centre, np.float32)
+    near = c + rng.uniform(-1.3, 1.3, (60000, 3)).astype(np.float32) * np.float32(radius)
+    with np.errstate(over="ignore"):
+        far = (rng.normal(size=(60000, 3)) * 10.0 ** rng.uniform(0, 38.5, (60000, 1))).astype(np.float32)
+    tiny = (rng.normal(size=(2000, 3)) * 10.0 ** rng.uniform(-45, -30, (2000, 1))).astype(np.float32)
+    special = np.array([[np.inf, 0, 0], [0, -np.inf, 1], [np.inf, np.inf, -np.inf], [np.nan, 1, 2], [1, np.nan, np.inf],
+                        [3.4e38, 3.4e38, 3.4e38], [-3.4e38, 1, 1], [0, 0, 0], [-0.0, -0.0, -0.0], [1e19, 1e19, 1e19], [2e19, 0, 0]], np.float32)
+    return np.ascontiguousarray(np.concatenate([near, far, tiny, special]).astype(np.float32))
+
+
+@pytest.mark.parametrize("flavour", ["exact", "fast"])
+@pytest.mark.parametrize("baked", [True, False])
+def test_carve_far_field_value_equals_the_full_sdf(ctx, flavour, baked):
+    """Far-field shortcut (include/rmb.h, lower_glsl.cpp pass 1b): at every position - near, far, overflowing,
+    infinite, NaN - the value the march kernels use (shortcut where A > U, sticky-guard evaluation with its
+    out-of-line fallback elsewhere) has the bits of the plain guarded sdf().  Both program variants: uniforms
+    baked (U folds to a literal) and dynamic (U evaluated on the device)."""
+    src = scene_source("guide")
+    custom = rm.default_custom_settings(src)
+    prog = ctx.program_cache.get_program(src, rm._lib.FLAVOUR_FAST if flavour == "fast" else rm._lib.FLAVOUR_EXACT, custom if baked else None)
+    assert isinstance(prog, rm.Program), prog
+    assert prog.has_carve()
+    if not baked:
+        from raymarching_engine_b200.uniforms import set_uniforms
+        set_uniforms(prog, custom)
+    pts = _carve_points(np.random.default_rng(7), (0, 0, 10), 4.0)
+    out = ctx.probe_carve(prog, pts)
+    via_march, A, U, guarded = out[:, 0], out[:, 1], out[:, 2], out[:, 3]
+    if flavour == "exact":
+        assert np.all(U == np.float32(0.21) * np.float32(3.0))        # 0.21 * sf of the coarsest grid
+    else:
+        np.testing.assert_allclose(U, 0.63, rtol=1e-6)
+    with np.errstate(invalid="ignore"):
+        far = A > U
+    if flavour == "exact":
+        np.testing.assert_array_equal(_canon(via_march), _canon(guarded))
+    else:
+        # the fast flavour contracts differently in different inlined copies; where the shortcut applies the
+        # value IS A, and A agrees with the full evaluation to rounding
+        np.testing.assert_array_equal(_canon(via_march[far]), _canon(A[far]))
+        ok = np.isfinite(guarded) & np.isfinite(via_march)
+        np.testing.assert_allclose(via_march[ok], guarded[ok], rtol=1e-5, atol=1e-5)
+    assert far.sum() > 30000 and (~far).sum() > 30000
+
+
+def test_carve_on_off_frames_are_bit_identical(ctx, monkeypatch):
+    """RMB_CARVE=0 builds the same programs without the shortcut: identical accumulators, depth, RGBA8 and
+    evaluation counts in both render modes; with the shortcut most evaluations of the default scene take it."""
+    src = scene_source("guide")
+    custom = rm.default_custom_settings(src)
+    outs = []
+    for carve in ("0", "1"):
+        monkeypatch.setenv("RMB_CARVE", carve)
+        c = rm.load_render_job_context(device=0)
+        try:
+            prog = c.program_cache.get_program(src, None, custom)
+            assert isinstance(prog, rm.Program), prog
+            assert prog.has_carve() == (carve == "1")
+            frames = []
+            for mode in ("preview", "full"):
+                s = rm.default_schema(src, custom, width=320, height=180, renderMode=mode, frameid=9950 + len(outs) * 10 + len(frames))
+                if mode == "full":
+                    s.lights = [rm.default_light()]
+                rm.reset_halton()
+                c.counters(reset=True)
+                fb = c.fbo.create(320, 180, s.render.frameid)
+                got = rm.run_job(s, c)
+                assert got["success"], got["why"]
+                frames.append((fb.read("color"), fb.read("depth"), fb.read("normalAndDofRadius"), fb.read("albedoAndDepth"), got["rgba8"].copy(), c.counters3(reset=True)))
+            outs.append(frames)
+        finally:
+            c.close()
+    for a, b in zip(outs[0], outs[1]):
+        np.testing.assert_array_equal(_canon(a[0]), _canon(b[0]))
+        np.testing.assert_array_equal(_canon(a[1]), _canon(b[1]))
+        for k in (2, 3, 4):
+            np.testing.assert_array_equal(a[k], b[k])
+        assert a[5][:2] == b[5][:2]                     # same number of SDF values and pixel-samples
+        assert a[5][2] == 0 and b[5][2] > 0.5 * b[5][0]  # ... most of them from the far-field path
