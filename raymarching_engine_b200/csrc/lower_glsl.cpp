@@ -449,11 +449,17 @@ LowerResult lower_scene(const std::string& glsl, const std::set<std::string>& co
         char bt; int bc;
         std::set<std::string> uniform_names;
         for (const UniformDecl& u : R.uniforms) uniform_names.insert(u.name);
-        bool has_pp = false, has_ref_params = false;
+        bool has_pp = false, has_ref_params = false, name_clash = false;
         for (size_t k = 0; k < n; k++) {
             if (T[k].kind == kPP && !T[k].drop) has_pp = true;
             if (live(k) && T[k].kind == kIdent && !T[k].text.empty() && T[k].text.back() == '&') has_ref_params = true;
+            // the helper names must be free
+            if (live(k) && T[k].kind == kIdent && (T[k].text.compare(0, 8, "rm_carve") == 0 || T[k].text == "rm_len0")) name_clash = true;
         }
+        // the analysis reasons about the built-ins: a scene function of the same name (GLSL ES 3.00 forbids it, C++
+        // member lookup would allow it) voids that
+        for (const std::string& f : R.functions)
+            if (pure_builtins.count(f) || uniform_type_info(f, &bt, &bc)) name_clash = true;
         // locate `float sdf ( [const] vec3 P ) {` at global scope (exactly one definition)
         size_t fn = n; int defs = 0;
         {
@@ -469,7 +475,7 @@ LowerResult lower_scene(const std::string& glsl, const std::set<std::string>& co
             }
         }
         do {
-            if (has_pp || has_ref_params || defs != 1) break;
+            if (has_pp || has_ref_params || name_clash || defs != 1) break;
             size_t ty = prev_live(fn);
             if (ty == n || T[ty].text != "float") break;
             size_t o = next_live(fn), q = next_live(o);

@@ -129,6 +129,10 @@ def test_rejected_contexts():
     assert not has_carve(good.replace("for (float i = 0.0; i < 4.0; i++)", "for (float i = 0.0; i < p.x; i++)"))
     assert not has_carve(good.replace("float sf = pow(s0, i);", "float sf = pow(s0, i); float R = 1.0;"))   # shadows a uniform
     assert not has_carve("float seedy = 0.0;\n" + good)                                       # impure scene: no wavefront pipeline at all
+    assert not has_carve("float length(vec3 v) { return -1.0; }\n" + good)                   # a scene function named like a built-in
+    assert not has_carve("float pow(float a, float b) { return a; }\n" + good)
+    assert not has_carve(good + "\nfloat rm_len0(vec3 v) { return 1.0; }\n")                 # the helper names must be free
+    assert not has_carve(good.replace("float dist", "float rm_carve_outer = 0.0; float dist"))
     # the switch
     os.environ["RMB_CARVE"] = "0"
     try:
