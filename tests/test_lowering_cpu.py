@@ -113,6 +113,28 @@ def test_compile_errors_are_values_with_gl_style_lines():
     assert st == _lib.RMB_ERR_FRAGMENT
 
 
+def test_translate_only_reports_scene_level_errors_without_compiling():
+    """rmb_translate_only: the lowering alone (milliseconds) gives the scene-level diagnostics and the translation unit;
+    errors only the C++ compiler can see (an undeclared identifier) need rmb_compile_only."""
+    def translate(src):
+        log = C.create_string_buffer(1 << 16)
+        out = C.create_string_buffer(2 << 20)
+        b = src.encode()
+        st = L.rmb_translate_only(b, len(b), _lib.FLAVOUR_EXACT, None, 0, log, len(log), out, len(out))
+        return st, log.value.decode(), out.value.decode()
+    st, log, tu = translate(scene_source("guide"))
+    assert st == _lib.RMB_OK and "rm_wf_march_preview_kernel" in tu and "__constant__ float fractalIterations;" in tu
+    st, log, _ = translate("vec3 sceneEmission(vec3 p) { return vec3(0.0); }\n")
+    assert st == _lib.RMB_ERR_FRAGMENT and "'sdf'" in log
+    st, log, _ = translate("uniform sampler2D tex;\nfloat sdf(vec3 p) { return 1.0; }")
+    assert st == _lib.RMB_ERR_FRAGMENT and "0:146" in log and "sampler" in log
+    st, log, _ = translate("float sdf(vec3 p) { return 1.0; ")
+    assert st == _lib.RMB_ERR_FRAGMENT
+    st, log, _ = translate("float sdf(vec3 p) {\n  return lenght(p) - 1.0;\n}\n")
+    assert st == _lib.RMB_OK          # not a lowering error
+    assert L.rmb_translate_only(None, 0, _lib.FLAVOUR_EXACT, None, 0, None, 0, None, 0) == _lib.RMB_ERR_INVALID
+
+
 def test_uniform_arrays_matrices_and_int_vectors():
     src = """
 uniform float weights[4];
