@@ -536,6 +536,24 @@ def run_b200(args):
                 "parity": "tolerance-checked, not bit-exact; see profiles/flavour_tolerance.json", "measured_tolerance": tol}
         except Exception as e:   # noqa: BLE001 - the headline must not depend on the optional second arm
             line["extra"]["fast_flavour"] = {"error": str(e)[:200]}
+    if rank == 0 and world == 1 and args.flavour == "exact" and not args.no_second_flavour and roofline.get("far_field_evals_share", 0) > 0:
+        # context for the roofline figure: the same workload with the far-field pipeline off (every ray marched by the
+        # one kernel, RMB_CARVE=0), measured the same way in a child process
+        cmd = [sys.executable, os.fspath(ROOT / "bench.py"), "--no-cpu-baseline", "--no-second-flavour",
+               "--steps", str(args.steps), "--warmup", str(args.warmup), "--width", str(W), "--height", str(H), "--mode", args.mode,
+               "--scene", args.scene, "--spp", str(args.spp), "--contexts", str(args.contexts), "--pipeline", args.pipeline]
+        if args.step_counts:
+            cmd += ["--step-counts", args.step_counts]
+        try:
+            out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, RMB_CARVE="0"))
+            f = json.loads(out.stdout.strip().splitlines()[-1])
+            line["extra"]["far_field_pipeline_off"] = {
+                "value": f["value"], "unit": f["unit"], "ms_per_step": f["ms_per_step"], "e2e": f["e2e"]["value"],
+                "roofline_frac": f["roofline"]["frac"], "roofline_achieved": f["roofline"]["achieved"],
+                "kernel_ms_per_step": f["roofline"]["kernel_ms_per_step"],
+                "note": "RMB_CARVE=0: bit-identical frames; the march kernel then also executes the 87 % of SDF evaluations whose value is the outer shape alone"}
+        except Exception as e:   # noqa: BLE001 - context only
+            line["extra"]["far_field_pipeline_off"] = {"error": str(e)[:200]}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         mpx, secs, cores, desc = cpu_reference_sample(W, H, args.mode, args.cpu_band_rows, None, args.scene, counts)
         line["cpu_baseline"] = {"value": mpx, "unit": "Mpx/s", "cores": cores, "kind": "port", "sample": desc, "seconds": secs}
