@@ -1,10 +1,11 @@
-// Rotated folding fractal ending in a box.
-// Restated from /root/reference/client/public/examples/rotation-fractal.glsl:2-35.
+
 uniform float fractalIterations;
-//@name="Fractal Iterations" @min=0 @max=20 @step=1 @sensitivity=0.01 @default=14
+//@name="Fractal Iterations" 
+//@min=0 @max=20 @step=1 @sensitivity=0.01 @default=14
 
 uniform float scaleFactor;
-//@name="Scale Factor" @min=0 @max=1.5 @step=0.001 @sensitivity=0.001 @default=0.5
+//@name="Scale Factor"
+//@min=0 @max=1.5 @step=0.001 @sensitivity=0.001 @default=0.5
 
 uniform vec3 angles;
 //@name="Angles" @step=0.001 @sensitivity=0.01 @default=0.4,0.4,0.4
@@ -12,7 +13,7 @@ uniform vec3 angles;
 uniform float offset;
 //@name="Offset" @step=0.001 @sensitivity=0.01 @default=1.2
 
-float sdf(vec3 position) {
+float sdf(vec3 position) {  
   vec3 transformedPos = position;
   for (float i = 0.0; i < fractalIterations; i++) {
      transformedPos /= scaleFactor;

@@ -1,10 +1,11 @@
-// Folded-space tree fractal (uses l-value swizzles `v.xy *= mat2(...)`).
-// Restated from /root/reference/client/public/examples/tree.glsl:2-36.
+
 uniform float fractalIterations;
-//@name="Fractal Iterations" @min=0 @max=20 @step=1 @sensitivity=0.01 @default=8
+//@name="Fractal Iterations" 
+//@min=0 @max=20 @step=1 @sensitivity=0.01 @default=8
 
 uniform float scaleFactor;
-//@name="Scale Factor" @min=0 @max=1.5 @step=0.001 @sensitivity=0.001 @default=0.7
+//@name="Scale Factor"
+//@min=0 @max=1.5 @step=0.001 @sensitivity=0.001 @default=0.7
 
 uniform vec3 angles;
 //@name="Angles" @step=0.001 @sensitivity=0.01 @default=2.9,-0.8,0.4
@@ -12,7 +13,7 @@ uniform vec3 angles;
 uniform float offset;
 //@name="Offset" @step=0.001 @sensitivity=0.01 @default=1.2
 
-float sdf(vec3 position) {
+float sdf(vec3 position) {  
   vec3 transformedPos = position;
   float minDist = 9999.0;
   for (float i = 0.0; i < fractalIterations; i++) {
