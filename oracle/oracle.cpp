@@ -365,12 +365,23 @@ struct Frag {
     vec3 trOrigin, trDir, trEnd;
     float trDeltaZ = 0.0f, trStepsTaken = 0.0f, trJitterX = 0.0f, trJitterY = 0.0f;
 
+    // event log of the full branch, for the float64 numpy restatement (tests/test_oracle_numpy_full.py):
+    // records [tag, v0, v1, ...] per event; tags are listed at orc_trace_full_pixel
+    std::vector<float>* trace = nullptr;
+    void tr(float tag, std::initializer_list<float> v) {
+        if (!trace) return;
+        trace->push_back(tag);
+        for (float x : v) trace->push_back(x);
+    }
+    void tr3(float tag, const vec3& a) { tr(tag, {a.x, a.y, a.z}); }
+
     Frag(const OrcUniforms& u, Scene& s, int w, int h) : U(u), S(s), W(w), H(h) {}
 
     const float PHI = 1.61803398874989484820459f;                   // raymarcher.frag:44
     const float PI = 3.141592f;                                     // raymarcher.frag:79
 
     float sdf(vec3 p) { sdfEvals++; return S.sdf(p); }
+    float trSdf(vec3 p) { const float v = sdf(p); tr(13.0f, {v, p.x, p.y, p.z}); return v; }
 
     float gold_noise(vec2 xy, float sd) {                           // raymarcher.frag:46-49
         return fract(tan(distance(xy * PHI, xy) * sd) * xy.x);
@@ -383,11 +394,14 @@ struct Frag {
         float twoPiU2 = 2.0f * PI * u2;
         float c = cos(twoPiU2);
         float s = sin(twoPiU2);
+        tr(2.0f, {u1, u2});
         return sqrt(-2.0f * log(u1)) * vec2(c, s);
     }
     float uniformSample() {                                         // raymarcher.frag:91-94
         seed += 0.131223f;
-        return gold_noise(texcoord * 1000.0f, fract(U.randNoise[0] + seed));
+        const float v = gold_noise(texcoord * 1000.0f, fract(U.randNoise[0] + seed));
+        tr(1.0f, {v});
+        return v;
     }
     vec3 sphereSample() {                                           // raymarcher.frag:96-101 (args left to right)
         vec2 a = boxMullerTransform();
@@ -453,6 +467,7 @@ struct Frag {
         }
 
         trOrigin = rayPosition; trDir = rayDirection; trDeltaZ = deltaZ;
+        tr(3.0f, {rayPosition.x, rayPosition.y, rayPosition.z, rayDirection.x, rayDirection.y, rayDirection.z});
         trJitterX = randomDirectionOffset.x; trJitterY = randomDirectionOffset.y;
         if (U.renderMode == 1) {                                    // preview branch :207-244
             float stepsTaken = 0.0f;
@@ -488,10 +503,13 @@ struct Frag {
 
         for (float i = 0.0f; i < U.reflections; i++) {              // :252
             vec3 oldRayPosition = rayPosition;
+            tr(10.0f, {i, oldRayPosition.x, oldRayPosition.y, oldRayPosition.z, rayDirection.x, rayDirection.y, rayDirection.z});
             rayPosition = castRay(rayPosition, rayDirection, U.raymarchingStepCountsArray[(int)i]);
+            tr3(11.0f, rayPosition);
             float pathLength = invExpDist(uniformSample(), U.fogDensity);
             currentLight += currentAlbedo * S.sceneEmission(rayPosition);
             vec3 normal = sceneNormal(rayPosition, 0.00001f);
+            tr3(12.0f, normal);
             float sss = S.sceneSubsurfaceScattering(rayPosition);
             float subsurfVolumetricSample = -1.0f / sss * log(1.0f - uniformSample());      // :266
             vec3 subsurfScatterDirection = normalize(mix(rayDirection, normalize(sphereSample()), 1.0f));
@@ -509,7 +527,7 @@ struct Frag {
                 diffuseCol = vec3(1.0f);
                 specularCol = vec3(1.0f);
                 prevRayDirection = rayDirection;
-            } else if (sdf(subsurfScatterFinalPos) > 0.001f) {      // :284-288
+            } else if (trSdf(subsurfScatterFinalPos) > 0.001f) {    // :284-288
                 currentAlbedo *= S.sceneSubsurfaceScatteringColor(rayPosition);
                 rayPosition = subsurfScatterFinalPos;
                 rayDirection = normalize(mix(rayDirection, sphereSample(), 1.0f));
@@ -536,6 +554,8 @@ struct Frag {
                 }
             }
             rayPosition += rayDirection * 0.001f;                   // :334
+            tr(14.0f, {rayPosition.x, rayPosition.y, rayPosition.z, rayDirection.x, rayDirection.y, rayDirection.z,
+                       currentAlbedo.x, currentAlbedo.y, currentAlbedo.z, currentLight.x, currentLight.y, currentLight.z});
 
             if (i == 0.0f) {                                        // :336-352
                 float depth = clamp(distance(rayPosition, position), 0.00001f, 100000000.0f);
@@ -548,6 +568,8 @@ struct Frag {
                 albedoAndDepth = vec4(currentAlbedo, depth) + prev.albedoAndDepth;
                 wroteAux = true;
                 hitDepth = depth;
+                tr(15.0f, {normalAndDofRadius.x, normalAndDofRadius.y, normalAndDofRadius.z, normalAndDofRadius.w,
+                           albedoAndDepth.x, albedoAndDepth.y, albedoAndDepth.z, albedoAndDepth.w});
             }
 
             for (int j = 0; j < U.lightCount; j++) {                // :354-373
@@ -557,6 +579,7 @@ struct Frag {
                 vec3 adjustedLightPosition = lightPosition + sphereSample() * lightSize;
                 vec3 directionToLight = normalize(adjustedLightPosition - rayPosition);
                 vec3 result = castRay(rayPosition, directionToLight, U.raymarchingStepCountsArray[(int)i]);
+                tr(16.0f, {(float)j, result.x, result.y, result.z});
                 if (distance(result, adjustedLightPosition) >= distance(rayPosition, adjustedLightPosition)) {
                     float r = max(0.0f, dot(directionToLight, reflect(prevRayDirection, normal)));
                     float roughness = S.sceneSpecularRoughness(rayPosition);
@@ -564,12 +587,14 @@ struct Frag {
                                     + prevAlbedo * specularCol * lightColor * roughness * roughness
                                           / (3.14159265f * pow(r * r * (roughness * roughness - 1.0f) + 1.0f, 2.0f));
                 }
+                tr3(17.0f, currentLight);
             }
         }
         (void)probabilityFactor;   // computed by the reference, never read
 
         if (U.blendMode == 0) fragColor = mix(vec4(currentLight * U.exposure, 1.0f), prev.color, U.blendWithPreviousFactor);   // :379-387
         else fragColor = vec4(currentLight * U.exposure, 1.0f) + prev.color;
+        tr(18.0f, {fragColor.x, fragColor.y, fragColor.z, fragColor.w});
     }
 };
 
@@ -705,6 +730,29 @@ static void trace_pixel_t(const float* custom, int ncustom, const OrcUniforms* U
     X("inline-default", SceneInlineDefault) \
     X("mandelbulb", SceneMandelbulb)
 
+// Event log of one full-mode (renderMode 0) invocation on zeroed previous texels, for the float64 numpy
+// restatement of the path tracer.  Events are [tag, payload...]:
+//   1 uniformSample() -> v            2 boxMullerTransform() inputs -> u1, u2      3 camera ray: origin, direction
+//  10 bounce i starts: i, oldRayPosition, rayDirection        11 castRay result           12 sceneNormal
+//  13 subsurface probe: sdf value, position                   14 after :334: rayPosition, rayDirection, currentAlbedo, currentLight
+//  15 bounce-0 attachments: normalAndDofRadius, albedoAndDepth
+//  16 light j: j, shadow castRay result                      17 currentLight after light j
+//  18 fragColor
+// Returns the number of floats the log holds (the first min(n, cap) are written to out).
+template <class Scene>
+static int trace_full_t(const float* custom, int ncustom, const OrcUniforms* U, int W, int H, int px, int py, float* out, int cap) {
+    Scene S;
+    if (ncustom == Scene::NU && ncustom) S.load(custom);
+    Frag<Scene> f(*U, S, W, H);
+    std::vector<float> log;
+    f.trace = &log;
+    f.texcoord = vec2(((float)px + 0.5f) / (float)W, ((float)py + 0.5f) / (float)H);
+    Accum prev;
+    prev.color = vec4(0.0f); prev.normalAndDofRadius = vec4(0.0f); prev.albedoAndDepth = vec4(0.0f);
+    f.main(prev);
+    for (size_t i = 0; i < log.size() && (int)i < cap; i++) out[i] = log[i];
+    return (int)log.size();
+}
 extern "C" {
 
 int orc_abi_version() { return 1; }
@@ -793,6 +841,13 @@ void orc_halton(int b, int n, double* out) {
 
 int orc_preview_exit_steps(const char* scene, const float* custom, int ncustom, const OrcUniforms* U, int W, int H, int* out) {
 #define X(name, T) if (!strcmp(scene, name)) { exit_steps_t<T>(custom, ncustom, U, W, H, out); return 0; }
+    ORC_SCENES(X)
+#undef X
+    return -1;
+}
+
+int orc_trace_full_pixel(const char* scene, const float* custom, int ncustom, const OrcUniforms* U, int W, int H, int px, int py, float* out, int cap) {
+#define X(name, T) if (!strcmp(scene, name)) return trace_full_t<T>(custom, ncustom, U, W, H, px, py, out, cap);
     ORC_SCENES(X)
 #undef X
     return -1;
