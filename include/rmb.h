@@ -199,6 +199,10 @@ rmb_status rmb_fb_copy_to_device(rmb_ctx* ctx, rmb_fb* fb, int which, void* dst_
 rmb_status rmb_counters_read(rmb_ctx* ctx, uint64_t out[2], int reset);
 /* the same plus out[2] = how many of out[0] took the far-field shortcut of a carved scene (below) */
 rmb_status rmb_counters_read3(rmb_ctx* ctx, uint64_t out[3], int reset);
+/* all 16 counter slots: [0..2] as above; [3..11] are filled only by programs built with RMB_PROFILE=1 in the
+ * environment (a measurement aid of the march kernel, see tools/march_timeline.py): warp-nanoseconds and warp-iterations
+ * before / after the work queue ran dry, warps, the longest warp, live lanes per iteration */
+rmb_status rmb_counters_read_all(rmb_ctx* ctx, uint64_t out[16], int reset);
 /* evaluates the scene's sdf() and material functions at n points: in n*3 floats, out n*17 floats
  * (diffuse rgb, specular rgb, roughness, subsurface, subsurfaceColor rgb, IOR, emission rgb, sdf, 0) */
 rmb_status rmb_probe(rmb_ctx* ctx, rmb_program* prog, const float* points_xyz, int n, float* out17);

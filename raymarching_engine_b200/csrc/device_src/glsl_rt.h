@@ -117,6 +117,7 @@ extern "C" {      // (re-declared in every namespace this header creates; same C
 __device__ __device_builtin__ float2 __ffma2_rn_impl(float2 x, float2 y, float2 z);
 __device__ __device_builtin__ float2 __fadd2_rn_impl(float2 x, float2 y);
 __device__ __device_builtin__ float2 __fmul2_rn_impl(float2 x, float2 y);
+__device__ __device_builtin__ float2 __fadd2_rd_impl(float2 x, float2 y);
 }
 typedef float2 f2_t;
 RM_HD f2_t f2_pack(float a, float b) { return make_float2(a, b); }
@@ -125,6 +126,7 @@ RM_HD f2_t f2_fma(f2_t a, f2_t b, f2_t c) { return __ffma2_rn_impl(a, b, c); }
 RM_HD f2_t f2_add(f2_t a, f2_t b) { return __fadd2_rn_impl(a, b); }
 RM_HD f2_t f2_sub(f2_t a, f2_t b) { return __fadd2_rn_impl(a, make_float2(-b.x, -b.y)); }   // a + (-b) == a - b bit for bit
 RM_HD f2_t f2_mul(f2_t a, f2_t b) { return __fmul2_rn_impl(a, b); }
+RM_HD f2_t f2_add_rd(f2_t a, f2_t b) { return __fadd2_rd_impl(a, b); }                      // FADD2.RM: round towards -inf
 #else
 #define GLSL_F32X2 0
 #endif
@@ -596,6 +598,73 @@ template <class S, class H2> RM_HD vec4 rm_rep0(const vec4& x, const S& s, const
     return vec4(rm_rep0(x.x, rm_c(s, 0), rm_c(h2, 0)), rm_rep0(x.y, rm_c(s, 1), rm_c(h2, 1)), rm_rep0(x.z, rm_c(s, 2), rm_c(h2, 2)),
                 rm_rep0(x.w, rm_c(s, 3), rm_c(h2, 3)));
 }
+
+// ---- bounded-floor sites (lower_glsl.cpp pass 2) ------------------------------------------------
+// rm_rep_b / rm_rep0_b are rm_rep / rm_rep0 at call sites whose operand is sdf()'s position parameter itself and
+// whose H1, S do not depend on the position.  Here - host, oracle-side test harness, every guarded evaluation -
+// they ARE rm_rep / rm_rep0.  The march kernels' fragment type overrides them with rm_rep_nf below.
+// rm_plim_site(acc, ..) lowers acc to the largest |coordinate| for which the site's floor() argument
+// q = (x + h1) * (1/s) is certainly within 2^22:  |q| <= (|x| + |h1|) / |s| * (1 + 2^-22), so
+// |x| <= 0.999 * 2^22 * |s| - |h1| suffices; a limit that is not a number (s or h1 NaN) becomes -1: never fast.
+template <class X, class H1, class S, class H2> RM_HD X rm_rep_b(const X& x, const H1& h1, const S& s, const H2& h2) { return rm_rep(x, h1, s, h2); }
+template <class X, class S, class H2> RM_HD X rm_rep0_b(const X& x, const S& s, const H2& h2) { return rm_rep0(x, s, h2); }
+RM_HD int rm_ncomp(float) { return 1; }
+RM_HD int rm_ncomp(const vec2&) { return 2; }
+RM_HD int rm_ncomp(const vec3&) { return 3; }
+RM_HD int rm_ncomp(const vec4&) { return 4; }
+RM_HD void rm_plim_lower(float& acc, float h1, float s) {
+    const float lim = g_sub(g_mul(4190109.0f, g_abs(s)), g_abs(h1));       // 0.999 * 2^22
+    if (!(lim == lim)) acc = -1.0f;
+    else if (lim < acc) acc = lim;
+}
+template <class X, class H1, class S, class H2> RM_HD X rm_plim_site(float& acc, const X& x, const H1& h1, const S& s, const H2&) {
+    for (int c = 0; c < rm_ncomp(x); c++) rm_plim_lower(acc, rm_c(h1, c), rm_c(s, c));
+    return X(0.0f);
+}
+template <class X, class S, class H2> RM_HD X rm_plim_site0(float& acc, const X& x, const S& s, const H2&) {
+    for (int c = 0; c < rm_ncomp(x); c++) rm_plim_lower(acc, 0.0f, rm_c(s, c));
+    return X(0.0f);
+}
+#if !GLSL_FAST && RM_DEVICE_CODE && !(defined(RM_PIN_ALT) && RM_PIN_ALT)
+// floor(q) on the FP32 pipe for |q| <= 2^22, +-inf and NaN (the caller has checked the range, see above):
+// round-DOWN add of 1.5 * 2^23 (ulp 1 there, so the sum is floor(q) + M exactly), subtract M.  The only
+// input whose result differs from floorf is -0 (gives +0); the mod() built on it then yields -0 instead of
+// +0 for x + h1 == -0, which the `- h2` that follows erases unless h2 is zero - so the sign is only
+// restored (LOP3) when h2 == 0 or NaN; with baked uniforms that test folds at compile time.
+RM_HD float g_floor_nf(float q, float h2) {
+    const float M = 12582912.0f;
+    float r = __fadd_rn(__fadd_rd(q, M), -M);
+    if (!(h2 != 0.0f) || !(h2 == h2)) r = __uint_as_float(__float_as_uint(r) | (__float_as_uint(q) & 0x80000000u));
+    return r;
+}
+RM_HD float rm_rep1_nf(float x, float h1, float s, float h2) {
+    const float a = g_add(x, h1);
+    return g_sub(g_fma(-s, g_floor_nf(g_mul(a, g_rcp(s)), h2), a), h2);
+}
+#if !GLSL_F32X2
+template <class H1, class S, class H2> RM_HD vec3 rm_rep_nf(const vec3& x, const H1& h1, const S& s, const H2& h2) {
+    return vec3(rm_rep1_nf(x.x, rm_c(h1, 0), rm_c(s, 0), rm_c(h2, 0)), rm_rep1_nf(x.y, rm_c(h1, 1), rm_c(s, 1), rm_c(h2, 1)),
+                rm_rep1_nf(x.z, rm_c(h1, 2), rm_c(s, 2), rm_c(h2, 2)));
+}
+#else
+// the packed rm_rep (above) with that floor: FADD2 / FMUL2 / FADD2.RM / FADD2 / FFMA2 / FADD2 for x and y
+template <class H1, class S, class H2> RM_HD vec3 rm_rep_nf(const vec3& x, const H1& h1, const S& s, const H2& h2) {
+    const float M = 12582912.0f;
+    const float sx = rm_c(s, 0), sy = rm_c(s, 1), sz = rm_c(s, 2);
+    const float h2x = rm_c(h2, 0), h2y = rm_c(h2, 1);
+    const f2_t A = f2_add(f2_pack(x.x, x.y), f2_pack(rm_c(h1, 0), rm_c(h1, 1)));
+    const f2_t Q = f2_mul(A, f2_pack(g_rcp(sx), g_rcp(sy)));
+    f2_t F = f2_add(f2_add_rd(Q, f2_pack(M, M)), f2_pack(-M, -M));
+    if (!(h2x != 0.0f) || !(h2x == h2x)) F.x = __uint_as_float(__float_as_uint(F.x) | (__float_as_uint(Q.x) & 0x80000000u));
+    if (!(h2y != 0.0f) || !(h2y == h2y)) F.y = __uint_as_float(__float_as_uint(F.y) | (__float_as_uint(Q.y) & 0x80000000u));
+    const f2_t E = f2_sub(f2_fma(f2_pack(-sx, -sy), F, A), f2_pack(h2x, h2y));
+    vec3 out;
+    f2_unpack(E, out.x, out.y);
+    out.z = rm_rep1_nf(x.z, rm_c(h1, 2), sz, rm_c(h2, 2));
+    return out;
+}
+#endif
+#endif
 
 RM_HD vec2 clamp(const vec2& v, float lo, float hi) { return vec2(clamp(v.x, lo, hi), clamp(v.y, lo, hi)); }
 RM_HD vec3 clamp(const vec3& v, float lo, float hi) { return vec3(clamp(v.x, lo, hi), clamp(v.y, lo, hi), clamp(v.z, lo, hi)); }

@@ -9,9 +9,8 @@
 // Arithmetic uses the exact policy of glsl_rt.h (single IEEE operations ptxas cannot fuse and
 // the shared rm_math.h exp/pow) so the bytes are identical to the CPU oracle's.
 //
-// Layout: one thread per pixel, consecutive threads along x; each thread writes one uchar4
-// (a warp writes one full 128-byte line).  Rows are this rank's LOCAL rows; the texcoord uses the
-// global row.  The blur reads neighbours from the local buffer, which is only correct when this
+// Layout: a thread presents four consecutive pixels of a row and writes them with one 128-bit store.
+// Rows are this rank's LOCAL rows; the texcoord uses the global row.  The blur reads neighbours from the local buffer, which is only correct when this
 // rank owns the whole frame (n_ranks == 1) or the blur radius is 0 (preview mode);
 // the host gathers the colour plane to one rank before presenting a blurred multi-GPU frame.
 #include <cuda_runtime.h>
@@ -29,14 +28,23 @@ __device__ __forceinline__ float h2f(unsigned short h) {
     return f;
 }
 
-__global__ void __launch_bounds__(256) rm_display_kernel(const float4* __restrict__ color, const ushort4* __restrict__ nd,
-                                                         uchar4* __restrict__ out, uchar4* __restrict__ gather, int W, int localRows, int H,
-                                                         int tileRows, int nRanks, int rank, float brightness) {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int ly = blockIdx.y;
-    if (x >= W || ly >= localRows) return;
-    const int t = ly / tileRows;
-    const int gy = (t * nRanks + rank) * tileRows + (ly - t * tileRows);
+// gamma + RGBA8 quantisation of display.frag:54,61 as a table search: byte = #{k : x >= T[k]}, T = the 255 thresholds
+// of device_src/display_gamma_table.inc - derived from, and verified for every float against, the binary64-evaluated
+// pow(x, 1/2.2) it replaces (tools/gen_gamma_table.cpp; three such pow() per pixel were ~80 % of this kernel's
+// instructions).  NaN and negative inputs compare false everywhere -> 0, like clamp(NaN -> 0).
+__device__ const unsigned int rm_gamma_bits[255] = {
+#include "device_src/display_gamma_table.inc"
+};
+__device__ __forceinline__ unsigned int gammaByte(const float* __restrict__ T, float x) {     // T[0] = -inf, T[1..255]
+    int k = 0;
+#pragma unroll
+    for (int step = 128; step >= 1; step >>= 1) k += (x >= T[k + step]) ? step : 0;
+    return (unsigned int)k;
+}
+
+// one pixel of the present pass -> packed RGBA8 (r in the low byte)
+__device__ __forceinline__ unsigned int displayPixel(const float4* __restrict__ color, const ushort4* __restrict__ nd, const float* __restrict__ T,
+                                                     int x, int ly, int gy, int W, int H, int tileRows, int nRanks, int rank, float brightness) {
     const size_t idx = (size_t)ly * (size_t)W + (size_t)x;
     const vec2 texcoord(g_div(g_add((float)x, 0.5f), (float)W), g_div(g_add((float)gy, 0.5f), (float)H));
     const float PI_D = 3.1415926535f;                                    // display.frag:9
@@ -78,7 +86,10 @@ __global__ void __launch_bounds__(256) rm_display_kernel(const float4* __restric
         for (float xo = -kernelSize; xo <= kernelSize; xo = g_add(xo, 1.0f)) {
             const vec2 offset(xo, y);
             const float texOffsetX = g_div(xo, (float)W);
-            const float factor = g_mul(norm, rmx::exp_ft(-g_div(dot(offset, offset), twoSigma2)));   // exp of the exact policy, table-driven coefficients
+            // the centre tap (the only one when kernelSize is 0: every preview-mode frame): exp(-0) is exactly 1 in the
+            // shared exp (rm_math.h dexp2_k: n = 0, f = 0, polynomial 1) and norm * 1 == norm, so the call is skipped
+            const float d2 = dot(offset, offset);
+            const float factor = (d2 == 0.0f) ? norm : g_mul(norm, rmx::exp_ft(-g_div(d2, twoSigma2)));   // exp of the exact policy, table-driven coefficients
             sampleCount = g_add(sampleCount, factor);
             const float uvX = g_add(texcoord.x, texOffsetX);
             const long long i = wrap(floor(g_mul(uvX, (float)W)), W);
@@ -87,21 +98,42 @@ __global__ void __launch_bounds__(256) rm_display_kernel(const float4* __restric
         }
     }
     avg /= sampleCount;
-    const vec4 base(vec3(avg.x, avg.y, avg.z) * brightness, 1.0f);
-    const float ig = g_div(1.0f, 2.2f);
-    const vec4 frag(rmx::pow_ft(base.x, ig), rmx::pow_ft(base.y, ig), rmx::pow_ft(base.z, ig), rmx::pow_ft(base.w, ig));   // :54
-    unsigned char b[4];
-    for (int cpt = 0; cpt < 4; cpt++) {
-        float v = frag[cpt];
-        if (isnan(v)) v = 0.0f;
-        v = clamp(v, 0.0f, 1.0f);
-        b[cpt] = (unsigned char)(int)floor(g_add(g_mul(v, 255.0f), 0.5f));
+    const vec3 base = vec3(avg.x, avg.y, avg.z) * brightness;
+    // :54 pow(vec4(base, 1), 1/2.2) and the RGBA8 conversion: alpha = pow(1, y) = 1 -> 255
+    return gammaByte(T, base.x) | (gammaByte(T, base.y) << 8) | (gammaByte(T, base.z) << 16) | 0xff000000u;
+}
+
+// Layout: a thread presents 4 horizontally adjacent pixels and writes them as ONE 128-bit store (a warp: four full
+// 128-byte lines); rows whose width is not a multiple of 4 finish with scalar stores.
+__global__ void __launch_bounds__(256) rm_display_kernel(const float4* __restrict__ color, const ushort4* __restrict__ nd,
+                                                         uchar4* __restrict__ out, uchar4* __restrict__ gather, int W, int localRows, int H,
+                                                         int tileRows, int nRanks, int rank, float brightness) {
+    __shared__ float T[256];
+    T[threadIdx.x] = threadIdx.x ? __uint_as_float(rm_gamma_bits[threadIdx.x - 1]) : __int_as_float(0xff800000);
+    __syncthreads();
+    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int ly = blockIdx.y;
+    if (x0 >= W || ly >= localRows) return;
+    const int t = ly / tileRows;
+    const int gy = (t * nRanks + rank) * tileRows + (ly - t * tileRows);
+    unsigned int px[4];
+    const int n = min(4, W - x0);
+    for (int k = 0; k < n; k++) px[k] = displayPixel(color, nd, T, x0 + k, ly, gy, W, H, tileRows, nRanks, rank, brightness);
+    const size_t idx = (size_t)ly * (size_t)W + (size_t)x0;
+    // fused tile gather (multi-GPU row-tile sharding): the same pixels go straight into the assembled
+    // full frame - usually rank 0's memory mapped over NVLink (CUDA IPC) - at their GLOBAL row.  Full 128-byte
+    // lines per warp, so the peer stores are fully coalesced; no separate collective moves pixels.
+    const size_t gidx = (size_t)gy * (size_t)W + (size_t)x0;
+    if (n == 4 && (W & 3) == 0) {
+        const uint4 v = make_uint4(px[0], px[1], px[2], px[3]);
+        *reinterpret_cast<uint4*>(out + idx) = v;
+        if (gather) *reinterpret_cast<uint4*>(gather + gidx) = v;
+    } else {
+        for (int k = 0; k < n; k++) {
+            reinterpret_cast<unsigned int*>(out)[idx + k] = px[k];
+            if (gather) reinterpret_cast<unsigned int*>(gather)[gidx + k] = px[k];
+        }
     }
-    out[idx] = make_uchar4(b[0], b[1], b[2], b[3]);
-    // fused tile gather (multi-GPU row-tile sharding): the same pixel goes straight into the assembled
-    // full frame - usually rank 0's memory mapped over NVLink (CUDA IPC) - at its GLOBAL row.  A warp
-    // writes one 128-byte line, so the peer stores are fully coalesced; no separate collective moves pixels.
-    if (gather) gather[(size_t)gy * (size_t)W + (size_t)x] = make_uchar4(b[0], b[1], b[2], b[3]);
 }
 
 }  // namespace disp
@@ -176,7 +208,7 @@ extern "C" cudaError_t rmb_launch_fp32_peak(float* scratch, int blocks, int iter
 
 extern "C" cudaError_t rmb_launch_display(const void* color, const void* nd, void* rgba8, void* gather, int W, int local_rows, int H,
                                           int tile_rows, int n_ranks, int rank, float brightness, cudaStream_t stream) {
-    dim3 block(256, 1, 1), grid((unsigned)((W + 255) / 256), (unsigned)local_rows, 1);
+    dim3 block(256, 1, 1), grid((unsigned)((W + 1023) / 1024), (unsigned)local_rows, 1);    // 4 pixels per thread
     xg::disp::rm_display_kernel<<<grid, block, 0, stream>>>((const float4*)color, (const ushort4*)nd, (uchar4*)rgba8, (uchar4*)gather, W,
                                                             local_rows, H, tile_rows, n_ranks, rank, brightness);
     return cudaGetLastError();

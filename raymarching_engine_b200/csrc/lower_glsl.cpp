@@ -424,7 +424,18 @@ LowerResult lower_scene(const std::string& glsl, const std::set<std::string>& co
         size_t ea_first = 0, ea_last = 0;           // token range of A
         size_t max_first = 0, max_close = 0;        // `max` .. its ')'
         std::vector<size_t> len_tokens;             // the accepted `length` identifiers
+        // bounded-floor analysis (pass 2): position-independent names of sdf's body, the return statement, and the
+        // domain-repetition call sites whose operand is the position parameter itself
+        std::set<std::string> clean;
+        size_t ret_tok = 0, ret_semi = 0;
+        std::vector<size_t> rep_sites;
     } carve;
+    static const std::set<std::string> pure_builtins = {
+        "pow", "exp", "exp2", "log", "log2", "sqrt", "inversesqrt", "abs", "sign", "floor", "ceil", "fract", "mod", "min", "max",
+        "clamp", "mix", "step", "smoothstep", "sin", "cos", "tan", "asin", "acos", "atan", "radians", "degrees", "length",
+        "distance", "dot", "cross", "normalize", "round", "trunc"};
+    std::set<std::string> uniform_names;
+    for (const UniformDecl& u : R.uniforms) uniform_names.insert(u.name);
     if (R.pure) {
         auto live = [&](size_t k) { return k < n && !T[k].drop && T[k].kind != kPP; };
         auto next_live = [&](size_t k) { k++; while (k < n && !live(k)) k++; return k; };
@@ -442,19 +453,14 @@ LowerResult lower_scene(const std::string& glsl, const std::set<std::string>& co
         auto is_for = [&](size_t k) { const std::string& w = T[k].text; return T[k].kind == kIdent && w.size() >= 3 && w.compare(w.size() - 3, 3, "for") == 0 && (w.size() == 3 || w[w.size() - 4] == ' '); };
         static const std::set<std::string> assign_ops = {"=", "+=", "-=", "*=", "/=", "%=", "&=", "|=", "^=", "<<=", ">>=", "++", "--"};
         static const std::set<std::string> banned = {"if", "else", "while", "do", "switch", "case", "default", "break", "continue", "discard", "goto", "struct"};
-        static const std::set<std::string> pure_builtins = {
-            "pow", "exp", "exp2", "log", "log2", "sqrt", "inversesqrt", "abs", "sign", "floor", "ceil", "fract", "mod", "min", "max",
-            "clamp", "mix", "step", "smoothstep", "sin", "cos", "tan", "asin", "acos", "atan", "radians", "degrees", "length",
-            "distance", "dot", "cross", "normalize", "round", "trunc"};
         char bt; int bc;
-        std::set<std::string> uniform_names;
-        for (const UniformDecl& u : R.uniforms) uniform_names.insert(u.name);
         bool has_pp = false, has_ref_params = false, name_clash = false;
         for (size_t k = 0; k < n; k++) {
             if (T[k].kind == kPP && !T[k].drop) has_pp = true;
             if (live(k) && T[k].kind == kIdent && !T[k].text.empty() && T[k].text.back() == '&') has_ref_params = true;
             // the helper names must be free
-            if (live(k) && T[k].kind == kIdent && (T[k].text.compare(0, 8, "rm_carve") == 0 || T[k].text == "rm_len0")) name_clash = true;
+            if (live(k) && T[k].kind == kIdent && (T[k].text.compare(0, 8, "rm_carve") == 0 || T[k].text == "rm_len0" || T[k].text.compare(0, 7, "rm_plim") == 0 ||
+                                                       T[k].text.compare(0, 8, "rm_floor") == 0 || T[k].text.compare(0, 6, "rm_rep") == 0)) name_clash = true;
         }
         // the analysis reasons about the built-ins: a scene function of the same name (GLSL ES 3.00 forbids it, C++
         // member lookup would allow it) voids that
@@ -754,6 +760,8 @@ LowerResult lower_scene(const std::string& glsl, const std::set<std::string>& co
             }
             if (bad) break;
             carve.ok = true;
+            carve.clean = clean;
+            carve.ret_tok = ret_tok; carve.ret_semi = semi_end;
             carve.m_name = m;
             carve.ea_first = eaf; carve.ea_last = eal;
             carve.max_first = max_tok; carve.max_close = mc;
@@ -850,8 +858,36 @@ LowerResult lower_scene(const std::string& glsl, const std::set<std::string>& co
                 size_t q = next_live(h2_last);
                 if (q < n && (T[q].text == "%" || T[q].text == "." || T[q].text == "[" || T[q].text == "(")) continue;
             }
-            if (last_add != n) { T[m].text = "rm_rep"; T[last_add].text = ","; }
-            else T[m].text = "rm_rep0";
+            // Bounded-floor sites.  In a carved scene (pass 1b: straight-line sdf body, parameter never written) a
+            // repetition whose operand is the position parameter ITSELF and whose H1 and S are position-independent
+            // becomes rm_rep_b / rm_rep0_b: the march kernels evaluate its floor() on the FP32 pipe without a range
+            // guard, having checked once per evaluation that |position| <= rm_floor_plim() - the largest coordinate
+            // for which every such site's floor argument stays within 2^22 (emitted below from the same H1 and S).
+            bool bounded = false;
+            if (carve.ok && m > carve.body_open && m < carve.body_close) {
+                const size_t x_end = last_add != n ? last_add : comma;
+                const size_t xf = next_live(open);
+                auto range_clean = [&](size_t first, size_t end) {      // identifiers of [first, end)
+                    char bt2; int bc2;
+                    for (size_t k = first; k < end; k = next_live(k)) {
+                        if (T[k].kind != kIdent) continue;
+                        size_t pv2 = prev_live(k);
+                        if (pv2 != n && T[pv2].text == ".") continue;
+                        const std::string& w = T[k].text;
+                        if (uniform_type_info(w, &bt2, &bc2)) continue;
+                        size_t nx = next_live(k);
+                        if (nx < n && T[nx].text == "(") { if (pure_builtins.count(w)) continue; return false; }
+                        if (carve.clean.count(w) || uniform_names.count(w)) continue;
+                        return false;
+                    }
+                    return true;
+                };
+                bounded = xf < x_end && T[xf].text == carve.param && next_live(xf) == x_end &&
+                          (last_add == n || range_clean(next_live(last_add), comma)) && range_clean(next_live(comma), close);
+            }
+            if (bounded) carve.rep_sites.push_back(m);
+            if (last_add != n) { T[m].text = bounded ? "rm_rep_b" : "rm_rep"; T[last_add].text = ","; }
+            else T[m].text = bounded ? "rm_rep0_b" : "rm_rep0";
             T[close].text = ",";
             T[minus].drop = true;
             T[h2_last].text += ")";
@@ -862,6 +898,7 @@ LowerResult lower_scene(const std::string& glsl, const std::set<std::string>& co
     // Works on a copy of the token texts; see LowerResult::body_packed and device_src/glsl_pk.h.
     std::vector<std::string> packed_text(n);
     for (size_t k = 0; k < n; k++) packed_text[k] = T[k].text;
+    for (size_t k : carve.rep_sites) packed_text[k] = T[k].text == "rm_rep_b" ? "rm_rep" : "rm_rep0";
     {
         auto live = [&](size_t k) { return k < n && !T[k].drop && T[k].kind != kPP; };
         auto next_live = [&](size_t k) { k++; while (k < n && !live(k)) k++; return k; };
@@ -992,6 +1029,28 @@ LowerResult lower_scene(const std::string& glsl, const std::set<std::string>& co
         }
         R.carve_text = "\nfloat rm_carve_outer(vec3 " + carve.param + ") { return" + outer + "; }\n" +
                        "float rm_carve_bound() { vec3 " + carve.param + " = vec3(0.0f);" + bound + " }\n";
+        if (!carve.rep_sites.empty()) {
+            // rm_floor_plim(): sdf's body once more with every bounded site replaced by rm_plim_site(rm_plim, ..), which
+            // lowers rm_plim to the site's coordinate limit (glsl_rt.h), and `return rm_plim` for the return statement
+            std::set<size_t> sites(carve.rep_sites.begin(), carve.rep_sites.end());
+            std::string plim;
+            for (size_t k = carve.body_open + 1; k < carve.body_close; k++) {
+                if (!live(k)) continue;
+                plim += ' ';
+                if (k == carve.ret_tok) { plim += "return rm_plim ;"; break; }
+                if (sites.count(k)) {
+                    plim += T[k].text == "rm_rep_b" ? "rm_plim_site" : "rm_plim_site0";
+                    // the '(' that follows is kept; the accumulator becomes the first argument
+                    size_t o = k + 1; while (o < n && !live(o)) o++;
+                    plim += " ( rm_plim ,";
+                    k = o;
+                    continue;
+                }
+                plim += lens.count(k) ? std::string("rm_len0") : T[k].text;
+            }
+            R.carve_text += "float rm_floor_plim() { float rm_plim = 3.0e38f; vec3 " + carve.param + " = vec3(0.0f);" + plim + " }\n";
+            R.floor_sites = (int)carve.rep_sites.size();
+        }
     }
     R.ok = true;
     return R;

@@ -32,6 +32,9 @@ struct LowerResult {
                                         // of an outer shape (max(A, -M)): definitions of rm_carve_outer(P) = A
                                         // and rm_carve_bound() = an upper bound of -M valid at every position,
                                         // so that sdf(P) == A bit for bit wherever A > bound (lower_glsl.cpp 1b)
+    int floor_sites = 0;                // > 0: carve_text also defines rm_floor_plim(), and that many domain repetitions of
+                                        // sdf() are emitted as rm_rep_b / rm_rep0_b (floor() without a range guard while
+                                        // every |position coordinate| <= rm_floor_plim(); lower_glsl.cpp pass 2)
 };
 
 // `constant_names`: uniforms that will be compile-time constants in this program variant (baked).

@@ -163,6 +163,12 @@ class RenderJobContext:                  # RenderJobExecutor.tsx:32-54
         L.rmb_counters_read3(self.handle, out, 1 if reset else 0)
         return int(out[0]), int(out[1]), int(out[2])
 
+    def counters_all(self, reset: bool = False):
+        """all 16 counter slots (rmb_counters_read_all; slots 3.. are filled by RMB_PROFILE=1 programs only)"""
+        out = (C.c_uint64 * 16)()
+        L.rmb_counters_read_all(self.handle, out, 1 if reset else 0)
+        return [int(v) for v in out]
+
     def probe_carve(self, program, points) -> np.ndarray:
         """n x 4: sdf as the march kernels evaluate it, outer shape A, bound U, guarded sdf (rmb_probe_carve)"""
         pts = np.ascontiguousarray(points, dtype=np.float32).reshape(-1, 3)

@@ -11,7 +11,7 @@ import re
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Union
 
-from .uniforms import UniformData
+from .uniform_types import UniformData
 
 # Validate.tsx:84-85
 UNIFORM_VARIABLE_RE = re.compile(r"^(u?int|float|[iu]?vec[234])\s+[a-zA-Z_][a-zA-Z_0-9]*")

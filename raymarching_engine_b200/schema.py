@@ -5,7 +5,7 @@ from __future__ import annotations
 from dataclasses import dataclass, field
 from typing import Dict, List, Sequence, Union
 
-from .uniforms import UniformData
+from .uniform_types import UniformData
 
 Vec3 = Sequence[float]
 

