@@ -236,8 +236,10 @@ def workload_config(args) -> dict:
             "frames_per_step": args.frames_per_step,
             "flavour": args.flavour, "pipeline": args.pipeline, "shard": args.shard if args.gpus > 1 else "none",
             "contexts_per_gpu": args.contexts, "gather": args.gather if (args.gpus > 1 and args.shard == "tiles") else "none",
-            "l2": "flushed before every frame (160 MiB in-stream device memset, inside the timed region); "
-                  "e2e alternates two framebuffer sets per context (40 B/px each) and reads every frame back",
+            "l2": "flushed between timed iterations: a 160 MiB in-stream device memset on every context's stream before each "
+                  "step (= batch of frames), inside the timed region; within a step the frames rotate through the contexts' "
+                  "framebuffer sets and ray planes (72 B/px per frame in flight); the kernel-alone roofline pass flushes before "
+                  "every frame; e2e alternates two framebuffer sets per context (40 B/px each) and reads every frame back",
             "steps_per_px_reference": ref_steps_per_px(args)}
 
 
@@ -300,6 +302,12 @@ class Rig:
         with torch.cuda.stream(stream):
             self.dist.gather(g["send"], g["recv"], dst=0)
 
+    def flush_l2(self, nctx=None):
+        """160 MiB memset on the stream of every context in use (in order with the frames around it)"""
+        for k in range(nctx or self.nctx):
+            with self.torch.cuda.stream(self.streams[k]):
+                self.flush_bufs[k].zero_()
+
     def device_frame(self, frame, flush=False, nctx=None):
         """one frame, everything resident in HBM (async): [L2 flush], uniforms, raymarch, display[, gather]"""
         k = frame % (nctx or self.nctx)
@@ -346,10 +354,11 @@ class Rig:
         self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return float(t.item())
 
-    def measure_device(self, first_frame, n_frames):
-        """n_frames enqueued back to back (the host runs ahead of the GPU), each preceded by an in-stream 160 MiB L2
-        flush that is INSIDE the timed region; one start event (GPU idle, recorded on every stream) to the last end
-        event.  Returns (total ms max over ranks, launches, (evals, pixel-samples, far evals))."""
+    def measure_device(self, first_frame, n_frames, frames_per_step=1):
+        """n_frames enqueued back to back (the host runs ahead of the GPU); before every step (frames_per_step frames)
+        an in-stream 160 MiB L2 flush on every context's stream, INSIDE the timed region; one start event (GPU idle,
+        recorded on every stream) to the last end event.  Returns (total ms max over ranks, launches, (evals,
+        pixel-samples, far evals))."""
         torch = self.torch
         for c in self.ctxs:
             c.sync()
@@ -361,7 +370,9 @@ class Rig:
         for e, st_ in zip(starts, self.streams):
             e.record(st_)
         for i in range(n_frames):
-            self.device_frame(first_frame + i, flush=True)
+            if i % max(1, frames_per_step) == 0:
+                self.flush_l2()
+            self.device_frame(first_frame + i)
         for e, st_ in zip(ends, self.streams):
             e.record(st_)
         self.barrier()
@@ -478,7 +489,7 @@ def run_b200(args):
 
     # ---- timed: device-resident, K steps of F frames
     n_frames = args.steps * F
-    total_ms, gpu_launches, (evals, pxs, far_evals) = rig.measure_device(args.warmup * F, n_frames)
+    total_ms, gpu_launches, (evals, pxs, far_evals) = rig.measure_device(args.warmup * F, n_frames, F)
     frames_all = n_frames * (1 if tiles else world)
     value = frames_all * W * H * args.spp / (total_ms * 1e-3) / 1e6     # pixel-samples per second, whole job
 
@@ -591,7 +602,7 @@ def run_b200(args):
             for i in range(3 * nctx + 2):
                 r3.device_frame(i, flush=True)
             n3 = args.config3_steps * f3
-            ms3, launches3, _c3 = r3.measure_device(16, n3)
+            ms3, launches3, _c3 = r3.measure_device(16, n3, f3)
             e3_s, _ = r3.measure_e2e(16, n3, False)
             line["config3_tiles"] = {
                 "workload": f"guide.glsl 3840x2160 preview, interleaved 16-row tiles over {world} GPU(s), gather fused into the display kernel's stores "
@@ -667,7 +678,7 @@ def main():
     ap.add_argument("--gather", default="fused", choices=["fused", "nccl"],
                     help="--shard tiles: fused = display kernel stores into rank 0's frame over NVLink (CUDA IPC); nccl = torch.distributed.gather")
     ap.add_argument("--pipeline", default="wavefront", choices=["wavefront", "megakernel"])
-    ap.add_argument("--contexts", type=int, default=2, help="contexts (streams) per GPU the independent frames are dealt to")
+    ap.add_argument("--contexts", type=int, default=3, help="contexts (streams) per GPU the independent frames are dealt to")
     ap.add_argument("--e2e-depth", action="store_true", help="the end-to-end arm also reads the fp32 depth plane back (8 B/px instead of 4)")
     ap.add_argument("--config3-steps", type=int, default=4, help="steps of the 4K row-tile configuration measured beside the headline (0 = skip)")
     ap.add_argument("--cpu-band-rows", type=int, default=360)

@@ -69,32 +69,42 @@ __device__ __forceinline__ unsigned int displayPixel(const float4* __restrict__ 
         long long v = (long long)f % n;
         return v < 0 ? v + n : v;
     };
-    for (float y = -kernelSize; y <= kernelSize; y = g_add(y, 1.0f)) {   // :42-50
-        // everything that depends on the row only, once per row (the same operations the shader repeats
-        // for every tap of the row)
-        const float texOffsetY = g_div(y, (float)H);
-        const float uvY = g_add(texcoord.y, texOffsetY);
-        const long long j = wrap(floor(g_mul(uvY, (float)H)), H);
-        // global row j -> local row (identity when this rank owns every row)
-        long long lj = j;
-        if (nRanks > 1) {
-            const long long tj = j / tileRows;
-            lj = (tj / nRanks) * tileRows + (j - tj * tileRows);
-            if (tj % nRanks != rank) lj = ly;   // not resident here (see header note)
-        }
-        const float4* __restrict__ row = color + (size_t)lj * (size_t)W;
-        for (float xo = -kernelSize; xo <= kernelSize; xo = g_add(xo, 1.0f)) {
-            const vec2 offset(xo, y);
-            const float texOffsetX = g_div(xo, (float)W);
-            // the centre tap (the only one when kernelSize is 0: every preview-mode frame): exp(-0) is exactly 1 in the
-            // shared exp (rm_math.h dexp2_k: n = 0, f = 0, polynomial 1) and norm * 1 == norm, so the call is skipped
-            const float d2 = dot(offset, offset);
-            const float factor = (d2 == 0.0f) ? norm : g_mul(norm, rmx::exp_ft(-g_div(d2, twoSigma2)));   // exp of the exact policy, table-driven coefficients
-            sampleCount = g_add(sampleCount, factor);
-            const float uvX = g_add(texcoord.x, texOffsetX);
-            const long long i = wrap(floor(g_mul(uvX, (float)W)), W);
-            const float4 c = row[i];
-            avg += vec4(c.x, c.y, c.z, c.w) * factor;
+    if (kernelSize == 0.0f) {
+        // One tap (every preview-mode frame; full mode without depth of field): y = xo = -+0, so both
+        // texture offsets are +-0, uv = texcoord, and floor(fl(fl((g + 0.5) / N) * N)) == g for every g + 0.5 < 2^22
+        // (two roundings of relative size 2^-24 move g + 0.5 by less than 0.5): the tap is the pixel itself.
+        // d2 = 0 -> factor = norm (see below).  The arithmetic on the tap is the loop's, operation for operation.
+        sampleCount = g_add(sampleCount, norm);
+        const float4 c = color[idx];
+        avg += vec4(c.x, c.y, c.z, c.w) * norm;
+    } else {
+        for (float y = -kernelSize; y <= kernelSize; y = g_add(y, 1.0f)) {   // :42-50
+            // everything that depends on the row only, once per row (the same operations the shader repeats
+            // for every tap of the row)
+            const float texOffsetY = g_div(y, (float)H);
+            const float uvY = g_add(texcoord.y, texOffsetY);
+            const long long j = wrap(floor(g_mul(uvY, (float)H)), H);
+            // global row j -> local row (identity when this rank owns every row)
+            long long lj = j;
+            if (nRanks > 1) {
+                const long long tj = j / tileRows;
+                lj = (tj / nRanks) * tileRows + (j - tj * tileRows);
+                if (tj % nRanks != rank) lj = ly;   // not resident here (see header note)
+            }
+            const float4* __restrict__ row = color + (size_t)lj * (size_t)W;
+            for (float xo = -kernelSize; xo <= kernelSize; xo = g_add(xo, 1.0f)) {
+                const vec2 offset(xo, y);
+                const float texOffsetX = g_div(xo, (float)W);
+                // the centre tap (the only one when kernelSize is 0: every preview-mode frame): exp(-0) is exactly 1 in the
+                // shared exp (rm_math.h dexp2_k: n = 0, f = 0, polynomial 1) and norm * 1 == norm, so the call is skipped
+                const float d2 = dot(offset, offset);
+                const float factor = (d2 == 0.0f) ? norm : g_mul(norm, rmx::exp_ft(-g_div(d2, twoSigma2)));   // exp of the exact policy, table-driven coefficients
+                sampleCount = g_add(sampleCount, factor);
+                const float uvX = g_add(texcoord.x, texOffsetX);
+                const long long i = wrap(floor(g_mul(uvX, (float)W)), W);
+                const float4 c = row[i];
+                avg += vec4(c.x, c.y, c.z, c.w) * factor;
+            }
         }
     }
     avg /= sampleCount;
