@@ -241,6 +241,50 @@ void rmb_device_free(rmb_ctx* ctx, void* p);
 void* rmb_host_alloc(size_t bytes);
 void rmb_host_free(void* p);
 
+/* ---- device groups: all GPUs of one box behind one handle -------------------------------------
+ * `ctx_create(device_ids[], n)` - one context that owns the streams, program cache and buffer pool of
+ * every device, reachable from a single-threaded host (client/src/index.tsx:236-263 pumps ONE doRenderJob generator;
+ * renderer/RenderJobExecutor.tsx:77-341).  A group is n member contexts in ONE process - member i renders the row
+ * tiles t (tile_rows rows each) with t % n == i (the reference's own image-space split is the
+ * `subdivisions` scissor loop, RenderJobExecutor.tsx:148-182) - and each call below is the single-device call of the
+ * same name fanned out to the members.  No torch, no NCCL: the assembled RGBA8 frame lives on member 0's device, the
+ * other devices store into it from their display kernels through peer access (cudaDeviceEnablePeerAccess, NVLink),
+ * and completion is ordered by cross-device events.  Frames that may blur (some sample drawn with renderMode != 1)
+ * scatter their colour / normal+dofRadius rows to member 0, which runs the display pass over the assembled planes.
+ * `devices` may name one device more than once (two members on one GPU: the same code path, without peer traffic).
+ * rmb_group_create returns NULL on failure; rmb_group_last_error(NULL) explains. */
+typedef struct rmb_group rmb_group;
+typedef struct rmb_group_program rmb_group_program;
+typedef struct rmb_group_fb rmb_group_fb;
+rmb_group* rmb_group_create(const int* devices, int n, int tile_rows);
+void rmb_group_destroy(rmb_group* group);
+const char* rmb_group_last_error(rmb_group* group);
+int rmb_group_size(rmb_group* group);
+/* member context i (borrowed): per-device inspection, counters, timing */
+rmb_ctx* rmb_group_ctx(rmb_group* group, int member);
+rmb_status rmb_group_sync(rmb_group* group);
+/* rmb_program_get on every member (one host thread per device); errors are values exactly as there */
+rmb_status rmb_group_program_get(rmb_group* group, const char* scene_glsl, size_t scene_len, int flavour,
+                                 const rmb_spec_uniform* spec, int n_spec, rmb_group_program** out_program,
+                                 char* err_type, char* infolog, size_t infolog_cap);
+rmb_program* rmb_group_program_member(rmb_group_program* prog, int member);
+rmb_status rmb_group_uniform_set(rmb_group_program* prog, const char* name, int type, int count, const void* data);
+rmb_status rmb_group_uniform_set_array(rmb_group_program* prog, const char* name, int type, int components,
+                                       int n_elements, const void* data);
+rmb_status rmb_group_uniform_matrix4(rmb_group_program* prog, const char* name, const float* m16_column_major);
+/* fbo.create / fbo.delete on every member (each keeps its own rows; pool semantics as rmb_fb_acquire) */
+rmb_group_fb* rmb_group_fb_acquire(rmb_group* group, int width, int height, int64_t frameid);
+void rmb_group_fb_release(rmb_group* group, int width, int height, int64_t frameid);
+rmb_fb* rmb_group_fb_member(rmb_group_fb* fb, int member);
+/* one sample: every member draws its rows of the scissor box (asynchronous) */
+rmb_status rmb_group_render_sample(rmb_group* group, rmb_group_program* prog, rmb_group_fb* fb, int sx, int sy, int sw, int sh);
+/* present(): display pass on every member + assembly on member 0; rgba8_host receives the WHOLE frame
+ * (width*height*4 bytes, row 0 = bottom), depth_host (optional) width*height floats.  Blocking, like rmb_present. */
+rmb_status rmb_group_present(rmb_group* group, rmb_group_fb* fb, float brightness, uint8_t* rgba8_host, float* depth_host);
+/* the same without the readback (asynchronous): *rgba8_device = the assembled frame on member 0's device, complete
+ * after rmb_group_sync and valid until the next present of this group */
+rmb_status rmb_group_present_device(rmb_group* group, rmb_group_fb* fb, float brightness, void** rgba8_device);
+
 #ifdef __cplusplus
 }
 #endif

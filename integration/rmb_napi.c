@@ -55,27 +55,33 @@ static napi_value LastError(napi_env env, napi_callback_info info) {
 
 /* programGet(ctx, sceneGlsl, flavour, spec[{name,type,data:number[]}]) ->
  *   {program: external} | {type: "fragment"|"program"|"general", infoLog}      ShaderCache.tsx:91-119 */
-static napi_value ProgramGet(napi_env env, napi_callback_info info) {
-    ARGS(4);
-    size_t len = 0; char* src = str(env, argv[1], &len);
-    uint32_t n_spec = 0; napi_get_array_length(env, argv[3], &n_spec);
-    rmb_spec_uniform* spec = (rmb_spec_uniform*)calloc(n_spec ? n_spec : 1, sizeof *spec);
-    char** names = (char**)calloc(n_spec ? n_spec : 1, sizeof *names);
-    for (uint32_t k = 0; k < n_spec; k++) {
-        napi_value e, f; napi_get_element(env, argv[3], k, &e);
-        napi_get_named_property(env, e, "name", &f); names[k] = str(env, f, NULL); spec[k].name = names[k];
-        napi_get_named_property(env, e, "type", &f); spec[k].type = i32(env, f);
+typedef struct { rmb_spec_uniform* spec; char** names; uint32_t n; } spec_list;
+static spec_list parse_spec(napi_env env, napi_value arr) {
+    spec_list l; l.n = 0;
+    napi_get_array_length(env, arr, &l.n);
+    l.spec = (rmb_spec_uniform*)calloc(l.n ? l.n : 1, sizeof *l.spec);
+    l.names = (char**)calloc(l.n ? l.n : 1, sizeof *l.names);
+    for (uint32_t k = 0; k < l.n; k++) {
+        napi_value e, f; napi_get_element(env, arr, k, &e);
+        napi_get_named_property(env, e, "name", &f); l.names[k] = str(env, f, NULL); l.spec[k].name = l.names[k];
+        napi_get_named_property(env, e, "type", &f); l.spec[k].type = i32(env, f);
         napi_get_named_property(env, e, "data", &f);
-        uint32_t c = 0; napi_get_array_length(env, f, &c); if (c > 4) c = 4; spec[k].count = (int)c;
+        uint32_t c = 0; napi_get_array_length(env, f, &c); if (c > 4) c = 4; l.spec[k].count = (int)c;
         for (uint32_t j = 0; j < c; j++) {
             napi_value x; napi_get_element(env, f, j, &x);
-            if (spec[k].type == RMB_UNIFORM_F) spec[k].data.f[j] = (float)f64(env, x);
-            else if (spec[k].type == RMB_UNIFORM_I) spec[k].data.i[j] = i32(env, x);
-            else { uint32_t u = 0; napi_get_value_uint32(env, x, &u); spec[k].data.u[j] = u; }
+            if (l.spec[k].type == RMB_UNIFORM_F) l.spec[k].data.f[j] = (float)f64(env, x);
+            else if (l.spec[k].type == RMB_UNIFORM_I) l.spec[k].data.i[j] = i32(env, x);
+            else { uint32_t u = 0; napi_get_value_uint32(env, x, &u); l.spec[k].data.u[j] = u; }
         }
     }
-    rmb_program* prog = NULL; char etype[16] = {0}; char* log = (char*)calloc(1, 1 << 16);
-    rmb_status st = rmb_program_get((rmb_ctx*)ext(env, argv[0]), src, len, i32(env, argv[2]), spec, (int)n_spec, &prog, etype, log, 1 << 16);
+    return l;
+}
+static void free_spec(spec_list l) {
+    for (uint32_t k = 0; k < l.n; k++) free(l.names[k]);
+    free(l.names); free(l.spec);
+}
+/* {program: external} on success, else the reference's ShaderError value {type, infoLog} */
+static napi_value program_result(napi_env env, rmb_status st, void* prog, const char* etype, const char* log) {
     napi_value out; napi_create_object(env, &out);
     if (st == RMB_OK) napi_set_named_property(env, out, "program", mk_ext(env, prog));
     else {
@@ -83,8 +89,16 @@ static napi_value ProgramGet(napi_env env, napi_callback_info info) {
         napi_create_string_utf8(env, log, NAPI_AUTO_LENGTH, &b);
         napi_set_named_property(env, out, "type", a); napi_set_named_property(env, out, "infoLog", b);
     }
-    for (uint32_t k = 0; k < n_spec; k++) free(names[k]);
-    free(names); free(spec); free(src); free(log);
+    return out;
+}
+static napi_value ProgramGet(napi_env env, napi_callback_info info) {
+    ARGS(4);
+    size_t len = 0; char* src = str(env, argv[1], &len);
+    spec_list l = parse_spec(env, argv[3]);
+    rmb_program* prog = NULL; char etype[16] = {0}; char* log = (char*)calloc(1, 1 << 16);
+    rmb_status st = rmb_program_get((rmb_ctx*)ext(env, argv[0]), src, len, i32(env, argv[2]), l.spec, (int)l.n, &prog, etype, log, 1 << 16);
+    napi_value out = program_result(env, st, prog, etype, log);
+    free_spec(l); free(src); free(log);
     return out;
 }
 
@@ -150,6 +164,88 @@ static napi_value PresentWait(napi_env env, napi_callback_info info) {
 }
 static napi_value Sync(napi_env env, napi_callback_info info) { ARGS(1); return mk_i32(env, rmb_sync((rmb_ctx*)ext(env, argv[0]))); }
 
+/* ---- device groups (include/rmb.h rmb_group_*): every GPU of the box behind one handle, so the single-threaded
+ * host of index.tsx:236-263 renders one frame on all of them; same call shapes as above with `group` for `ctx`.
+ * groupCreate(devices: number[], tileRows) -> external | undefined */
+static napi_value GroupCreate(napi_env env, napi_callback_info info) {
+    ARGS(2);
+    uint32_t n = 0; napi_get_array_length(env, argv[0], &n);
+    int* dev = (int*)calloc(n ? n : 1, sizeof *dev);
+    for (uint32_t k = 0; k < n; k++) { napi_value e; napi_get_element(env, argv[0], k, &e); dev[k] = i32(env, e); }
+    rmb_group* g = rmb_group_create(dev, (int)n, i32(env, argv[1]));
+    free(dev);
+    return mk_ext(env, g);
+}
+static napi_value GroupDestroy(napi_env env, napi_callback_info info) { ARGS(1); rmb_group_destroy((rmb_group*)ext(env, argv[0])); return NULL; }
+static napi_value GroupLastError(napi_env env, napi_callback_info info) {
+    ARGS(1);
+    napi_valuetype t; napi_typeof(env, argv[0], &t);
+    const char* s = rmb_group_last_error(t == napi_external ? (rmb_group*)ext(env, argv[0]) : NULL);
+    napi_value v; napi_create_string_utf8(env, s ? s : "", NAPI_AUTO_LENGTH, &v); return v;
+}
+static napi_value GroupSize(napi_env env, napi_callback_info info) { ARGS(1); return mk_i32(env, rmb_group_size((rmb_group*)ext(env, argv[0]))); }
+static napi_value GroupSync(napi_env env, napi_callback_info info) { ARGS(1); return mk_i32(env, rmb_group_sync((rmb_group*)ext(env, argv[0]))); }
+static napi_value GroupProgramGet(napi_env env, napi_callback_info info) {
+    ARGS(4);
+    size_t len = 0; char* src = str(env, argv[1], &len);
+    spec_list l = parse_spec(env, argv[3]);
+    rmb_group_program* prog = NULL; char etype[16] = {0}; char* log = (char*)calloc(1, 1 << 16);
+    rmb_status st = rmb_group_program_get((rmb_group*)ext(env, argv[0]), src, len, i32(env, argv[2]), l.spec, (int)l.n, &prog, etype, log, 1 << 16);
+    napi_value out = program_result(env, st, prog, etype, log);
+    free_spec(l); free(src); free(log);
+    return out;
+}
+static napi_value GroupUniformSet(napi_env env, napi_callback_info info) {
+    ARGS(5); char* name = str(env, argv[1], NULL);
+    rmb_status st = rmb_group_uniform_set((rmb_group_program*)ext(env, argv[0]), name, i32(env, argv[2]), i32(env, argv[3]), typed(env, argv[4]));
+    free(name); return mk_i32(env, st);
+}
+static napi_value GroupUniformSetArray(napi_env env, napi_callback_info info) {
+    ARGS(6); char* name = str(env, argv[1], NULL);
+    rmb_status st = rmb_group_uniform_set_array((rmb_group_program*)ext(env, argv[0]), name, i32(env, argv[2]), i32(env, argv[3]), i32(env, argv[4]), typed(env, argv[5]));
+    free(name); return mk_i32(env, st);
+}
+static napi_value GroupUniformMatrix4(napi_env env, napi_callback_info info) {
+    ARGS(3); char* name = str(env, argv[1], NULL);
+    rmb_status st = rmb_group_uniform_matrix4((rmb_group_program*)ext(env, argv[0]), name, (const float*)typed(env, argv[2]));
+    free(name); return mk_i32(env, st);
+}
+static napi_value GroupFbAcquire(napi_env env, napi_callback_info info) {
+    ARGS(4);
+    return mk_ext(env, rmb_group_fb_acquire((rmb_group*)ext(env, argv[0]), i32(env, argv[1]), i32(env, argv[2]), (int64_t)f64(env, argv[3])));
+}
+static napi_value GroupFbRelease(napi_env env, napi_callback_info info) {
+    ARGS(4); rmb_group_fb_release((rmb_group*)ext(env, argv[0]), i32(env, argv[1]), i32(env, argv[2]), (int64_t)f64(env, argv[3])); return NULL;
+}
+static napi_value GroupRenderSample(napi_env env, napi_callback_info info) {
+    ARGS(7);
+    return mk_i32(env, rmb_group_render_sample((rmb_group*)ext(env, argv[0]), (rmb_group_program*)ext(env, argv[1]), (rmb_group_fb*)ext(env, argv[2]),
+                                               i32(env, argv[3]), i32(env, argv[4]), i32(env, argv[5]), i32(env, argv[6])));
+}
+/* groupPresent(group, fb, brightness, Uint8Array rgba8 (whole frame), Float32Array depth | null) */
+static napi_value GroupPresent(napi_env env, napi_callback_info info) {
+    ARGS(5);
+    napi_valuetype t; napi_typeof(env, argv[4], &t);
+    return mk_i32(env, rmb_group_present((rmb_group*)ext(env, argv[0]), (rmb_group_fb*)ext(env, argv[1]), (float)f64(env, argv[2]),
+                                         (uint8_t*)typed(env, argv[3]), t == napi_object ? (float*)typed(env, argv[4]) : NULL));
+}
+/* multi-process alternative (one context per process, frame assembled in rank 0's buffer over CUDA IPC):
+ * setGatherTarget(ctx, external | null, bytes), fbScatterRows(ctx, fb, which, external), displayPlanes(ctx, color, nd, out, w, h, brightness) */
+static napi_value SetGatherTarget(napi_env env, napi_callback_info info) {
+    ARGS(3);
+    napi_valuetype t; napi_typeof(env, argv[1], &t);
+    return mk_i32(env, rmb_ctx_set_gather_target((rmb_ctx*)ext(env, argv[0]), t == napi_external ? ext(env, argv[1]) : NULL, (size_t)f64(env, argv[2])));
+}
+static napi_value FbScatterRows(napi_env env, napi_callback_info info) {
+    ARGS(4);
+    return mk_i32(env, rmb_fb_scatter_rows((rmb_ctx*)ext(env, argv[0]), (rmb_fb*)ext(env, argv[1]), i32(env, argv[2]), ext(env, argv[3])));
+}
+static napi_value DisplayPlanes(napi_env env, napi_callback_info info) {
+    ARGS(7);
+    return mk_i32(env, rmb_display_planes((rmb_ctx*)ext(env, argv[0]), ext(env, argv[1]), ext(env, argv[2]), ext(env, argv[3]),
+                                          i32(env, argv[4]), i32(env, argv[5]), (float)f64(env, argv[6])));
+}
+
 #define EXPORT(name, fn) do { napi_value f; napi_create_function(env, name, NAPI_AUTO_LENGTH, fn, NULL, &f); napi_set_named_property(env, exports, name, f); } while (0)
 static napi_value Init(napi_env env, napi_value exports) {
     EXPORT("ctxCreate", CtxCreate); EXPORT("ctxDestroy", CtxDestroy); EXPORT("lastError", LastError);
@@ -157,6 +253,12 @@ static napi_value Init(napi_env env, napi_value exports) {
     EXPORT("uniformMatrix4", UniformMatrix4); EXPORT("fbAcquire", FbAcquire); EXPORT("fbRelease", FbRelease);
     EXPORT("fbLocalRows", FbLocalRows); EXPORT("renderSample", RenderSample); EXPORT("present", Present);
     EXPORT("presentAsync", PresentAsync); EXPORT("presentWait", PresentWait); EXPORT("sync", Sync);
+    EXPORT("groupCreate", GroupCreate); EXPORT("groupDestroy", GroupDestroy); EXPORT("groupLastError", GroupLastError);
+    EXPORT("groupSize", GroupSize); EXPORT("groupSync", GroupSync); EXPORT("groupProgramGet", GroupProgramGet);
+    EXPORT("groupUniformSet", GroupUniformSet); EXPORT("groupUniformSetArray", GroupUniformSetArray);
+    EXPORT("groupUniformMatrix4", GroupUniformMatrix4); EXPORT("groupFbAcquire", GroupFbAcquire);
+    EXPORT("groupFbRelease", GroupFbRelease); EXPORT("groupRenderSample", GroupRenderSample); EXPORT("groupPresent", GroupPresent);
+    EXPORT("setGatherTarget", SetGatherTarget); EXPORT("fbScatterRows", FbScatterRows); EXPORT("displayPlanes", DisplayPlanes);
     return exports;
 }
 NAPI_MODULE(NODE_GYP_MODULE_NAME, Init)

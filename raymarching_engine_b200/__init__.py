@@ -9,8 +9,10 @@ import fails if the library has not been built and there is no CPU fallback.
 from . import _lib  # noqa: F401  (raises ImportError when the CUDA library is missing)
 from ._lib import FLAVOUR_EXACT, FLAVOUR_EXACT_ALT, FLAVOUR_FAST
 from .executor import (FramebufferInfo, Program, RenderJobContext, ShaderError, builtin_uniforms, context_error,
-                       do_render_job, load_render_job_context, make_presenter, render_frames, reset_halton, run_job,
+                       do_render_job, load_render_job_context, make_presenter, render_frames, reset_halton,
+                       reset_specialization_history, run_job,
                        upload_sample_uniforms)
+from .group import RenderJobGroup, group_error, load_render_job_group
 from .halton import halton
 from .params import CustomShaderParam, CustomShaderParamError, default_custom_settings, get_custom_shader_params
 from .schema import (Camera, Dof, Orthographic, Panoramic, Perspective, PointLight, Render, RenderJobSchema, SunLight,

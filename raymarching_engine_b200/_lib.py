@@ -25,6 +25,9 @@ EXPORTED_SYMBOLS = [
     "rmb_render_sample", "rmb_present", "rmb_present_device", "rmb_present_async", "rmb_present_wait", "rmb_fb_device_ptr", "rmb_fb_plane_bytes",
     "rmb_fb_read", "rmb_fb_write", "rmb_fb_copy_to_device", "rmb_counters_read", "rmb_counters_read3", "rmb_counters_read_all", "rmb_program_has_carve", "rmb_probe_carve", "rmb_probe", "rmb_compile_only", "rmb_translate_only", "rmb_host_alloc", "rmb_device_alloc", "rmb_device_free",
     "rmb_host_free", "rmb_measure_fp32_peak", "rmb_measure_fp32x2_peak", "rmb_owned_rows_below",
+    "rmb_group_create", "rmb_group_destroy", "rmb_group_last_error", "rmb_group_size", "rmb_group_ctx", "rmb_group_sync", "rmb_group_program_get",
+    "rmb_group_program_member", "rmb_group_uniform_set", "rmb_group_uniform_set_array", "rmb_group_uniform_matrix4", "rmb_group_fb_acquire",
+    "rmb_group_fb_release", "rmb_group_fb_member", "rmb_group_render_sample", "rmb_group_present", "rmb_group_present_device",
 ]
 
 
@@ -97,6 +100,23 @@ def _load() -> C.CDLL:
         "rmb_device_alloc": (vp, [vp, sz]),
         "rmb_device_free": (None, [vp, vp]),
         "rmb_host_free": (None, [vp]),
+        "rmb_group_create": (vp, [C.POINTER(i), i, i]),
+        "rmb_group_destroy": (None, [vp]),
+        "rmb_group_last_error": (cp, [vp]),
+        "rmb_group_size": (i, [vp]),
+        "rmb_group_ctx": (vp, [vp, i]),
+        "rmb_group_sync": (i, [vp]),
+        "rmb_group_program_get": (i, [vp, cp, sz, i, C.POINTER(SpecUniform), i, C.POINTER(vp), cp, cp, sz]),
+        "rmb_group_program_member": (vp, [vp, i]),
+        "rmb_group_uniform_set": (i, [vp, cp, i, i, vp]),
+        "rmb_group_uniform_set_array": (i, [vp, cp, i, i, i, vp]),
+        "rmb_group_uniform_matrix4": (i, [vp, cp, C.POINTER(f)]),
+        "rmb_group_fb_acquire": (vp, [vp, i, i, C.c_int64]),
+        "rmb_group_fb_release": (None, [vp, i, i, C.c_int64]),
+        "rmb_group_fb_member": (vp, [vp, i]),
+        "rmb_group_render_sample": (i, [vp, vp, vp, i, i, i, i]),
+        "rmb_group_present": (i, [vp, vp, f, vp, vp]),
+        "rmb_group_present_device": (i, [vp, vp, f, C.POINTER(vp)]),
     }
     for name, (res, args) in proto.items():
         fn = getattr(lib, name)

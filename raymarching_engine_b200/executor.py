@@ -14,6 +14,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from dataclasses import dataclass
 from typing import Callable, Dict, Generator, Optional
 
@@ -125,7 +126,7 @@ class _ProgramCache:
 
 
 class RenderJobContext:                  # RenderJobExecutor.tsx:32-54
-    def __init__(self, handle: int, device: int, rank: int, n_ranks: int, tile_rows: int, flavour: int, specialize: bool):
+    def __init__(self, handle: int, device: int, rank: int, n_ranks: int, tile_rows: int, flavour: int, specialize):
         self.handle = handle
         self.device, self.rank, self.n_ranks, self.tile_rows = device, rank, n_ranks, tile_rows
         self.flavour, self.specialize = flavour, specialize
@@ -191,6 +192,10 @@ class RenderJobContext:                  # RenderJobExecutor.tsx:32-54
             self._pinned_cache[k] = buf
         return buf[1]
 
+    def render_sample(self, program: Program, fb: FramebufferInfo, x: int, y: int, w: int, h: int) -> int:
+        """gl.scissor(x, y, w, h) + the raymarcher draw + blit of one sample (RenderJobExecutor.tsx:181-326); status"""
+        return L.rmb_render_sample(self.handle, program.handle, fb.handle, x, y, w, h)
+
     def present(self, fb: FramebufferInfo, brightness: float, want_depth: bool = True, readback: bool = True):
         """display pass (+ readback into pinned host memory): (rgba8[local_rows, W, 4] uint8,
         depth[local_rows, W] float32 | None).  The arrays are views of buffers reused by the next
@@ -242,10 +247,22 @@ class RenderJobContext:                  # RenderJobExecutor.tsx:32-54
 
 
 def load_render_job_context(device: int = 0, rank: int = 0, n_ranks: int = 1, tile_rows: int = 16,
-                            flavour: int = _lib.FLAVOUR_EXACT, specialize: bool = True,
+                            flavour: int = _lib.FLAVOUR_EXACT, specialize=None,
                             pipeline: str = "wavefront") -> Optional[RenderJobContext]:
     """loadRenderJobContext(gl) (LoadRenderJobContext.tsx:268-287): returns None when any piece
-    of the context cannot be created (the reference returns undefined)."""
+    of the context cannot be created (the reference returns undefined).
+
+    specialize: how do_render_job treats schema.customShaderParameters (in the reference a free gl.uniform call,
+    RenderJobExecutor.tsx:266).  "auto" (default): plain dynamic uniforms until the same values have been submitted
+    for SPECIALIZE_AFTER consecutive jobs of that scene, then a program variant with the values baked in (loops
+    unroll, pow(uniform, i) folds); a value that changes - a slider being dragged, an animated parameter - falls
+    back to the dynamic variant at once and never costs a compile.  True / "always": bake from the first job on.
+    False / "never": always dynamic.  None: the RMB_SPECIALIZE environment variable (auto | always | never), default
+    "auto".  The library keeps at most RMB_VARIANT_CAP variants per scene (LRU)."""
+    if specialize is None:
+        specialize = os.environ.get("RMB_SPECIALIZE", "auto")
+    if specialize not in (True, False, "auto", "always", "never"):
+        raise ValueError(f"specialize={specialize!r}: expected auto | always | never")
     h = L.rmb_ctx_create(device, rank, n_ranks, tile_rows)
     if not h:
         return None
@@ -322,6 +339,33 @@ def upload_sample_uniforms(program: Program, schema: RenderJobSchema, rand_noise
 
 PresentFn = Callable[[RenderJobContext, RenderJobSchema, FramebufferInfo, int], None]
 
+# "auto" specialisation: jobs of a scene whose custom parameters have not changed for this many consecutive jobs
+# (counted over all contexts of the process: stability is a property of the job stream) get the baked variant
+SPECIALIZE_AFTER = 3
+_spec_streak: Dict[int, list] = {}       # hash(scene source) -> [signature of the custom values, consecutive jobs]
+
+
+def reset_specialization_history() -> None:
+    """Test hook: forget which custom-parameter values have been seen."""
+    _spec_streak.clear()
+
+
+def _specialize_now(context: RenderJobContext, schema: RenderJobSchema) -> bool:
+    mode = context.specialize
+    if mode is True or mode == "always":
+        return True
+    if mode is False or mode == "never" or mode is None:
+        return False
+    sig = tuple(sorted((name, d.type, tuple(float(v) for v in d.data)) for name, d in schema.customShaderParameters.items()))
+    key = hash(schema.sdfShaderSource)
+    st = _spec_streak.get(key)
+    if st is None or st[0] != sig:
+        st = _spec_streak[key] = [sig, 0]
+        if len(_spec_streak) > 64:
+            _spec_streak.pop(next(iter(_spec_streak)))
+    st[1] += 1
+    return st[1] >= SPECIALIZE_AFTER
+
 
 def do_render_job(schema: RenderJobSchema, context: RenderJobContext):
     """doRenderJob (RenderJobExecutor.tsx:77-341).  Returns a function that takes the `present`
@@ -334,9 +378,9 @@ def do_render_job(schema: RenderJobSchema, context: RenderJobContext):
             yield  # pragma: no cover
         return failed
 
-    spec = dict(schema.customShaderParameters) if context.specialize else None
+    spec = dict(schema.customShaderParameters) if _specialize_now(context, schema) else None
     program = context.program_cache.get_program(schema.sdfShaderSource, None, spec)          # :121-127
-    if not isinstance(program, Program):
+    if isinstance(program, ShaderError):
         def failed(_present):
             return {"success": False, "why": program}                                        # :129-136
             yield  # pragma: no cover
@@ -359,7 +403,7 @@ def do_render_job(schema: RenderJobSchema, context: RenderJobContext):
                     upload_sample_uniforms(program, schema, rand_noise)
                     # gl.scissor(x1, y1, x2, y2): the reference passes the far corner where GL expects
                     # width/height (RenderJobExecutor.tsx:182); reproduced as is.
-                    st = L.rmb_render_sample(context.handle, program.handle, framebuffers.handle, x1, y1, x2, y2)   # :299 + blit :301-326
+                    st = context.render_sample(program, framebuffers, x1, y1, x2, y2)                         # :299 + blit :301-326
                     if st != _lib.RMB_OK:
                         return {"success": False, "why": _gen_err(context.last_error())}
                     samples_rendered_so_far += 1

@@ -40,8 +40,20 @@ for frame, mode in enumerate(["preview", "full"]):
         g.complete(ctx)
     else:
         rm._lib.lib.rmb_ctx_set_gather_target(ctx.handle, None, 0)
-        out = rm.run_job(s, ctx)     # accumulators of this rank's tiles
+        # accumulators of this rank's tiles; no present on the member context (a tile-owning context refuses to present
+        # a frame that may blur: the display pass would read rows it does not hold)
+        gen = rm.do_render_job(s, ctx)(lambda *a: None)
+        try:
+            while True:
+                next(gen)
+        except StopIteration as stop:
+            out = stop.value
         assert out["success"], out["why"]
+        try:
+            ctx.present(fb, 1.0)
+            raise SystemExit("present of a blurred tile frame must be refused")
+        except RuntimeError as e:
+            assert "neighbour rows" in str(e), e
         g.scatter(ctx, fb, frame)    # colour + normal/dofRadius rows -> rank 0's full-frame planes
         g.complete(ctx)
         if rank == 0:

@@ -691,3 +691,82 @@ def test_carve_on_off_frames_are_bit_identical(ctx, monkeypatch):
         # ... a large part of them from the far-field path (the march kernel spends one full evaluation per ray on finding
         # out that the ray has left the near field, so at this small size the share is a little under one half)
         assert a[5][2] == 0 and b[5][2] > 0.3 * b[5][0]
+
+
+def test_auto_specialisation_switches_variant_after_stable_jobs_and_keeps_the_bits():
+    """custom uniforms are dynamic (a free gl.uniform in the reference, RenderJobExecutor.tsx:266) until
+    the same values have been submitted SPECIALIZE_AFTER jobs in a row; a changed value goes back to the dynamic
+    variant without a compile; every variant renders the same bits."""
+    from raymarching_engine_b200 import executor as ex
+    c = rm.load_render_job_context(device=0, specialize="auto")
+    try:
+        ex.reset_specialization_history()
+        s = _schema("guide", 96, 54, "preview")
+        frames = []
+        for k in range(ex.SPECIALIZE_AFTER + 1):
+            got, _planes, _acc, want = _render_both(c, "guide", s)
+            frames.append(got["rgba8"])
+            np.testing.assert_array_equal(got["rgba8"], want)
+            # jobs 1 .. SPECIALIZE_AFTER-1 ran on the dynamic variant (bigSphereSize is a settable uniform there),
+            # the later ones on the baked one (setting another value is refused)
+            dyn = c.program_cache.get_program(s.sdfShaderSource, None, None)
+            rm.set_uniforms(dyn, {"bigSphereSize": s.customShaderParameters["bigSphereSize"]})
+        for f in frames[1:]:
+            np.testing.assert_array_equal(f, frames[0])
+        st = ex._spec_streak[hash(s.sdfShaderSource)]
+        assert st[1] == ex.SPECIALIZE_AFTER + 1
+        # a slider moves: the streak restarts and the job runs on the dynamic variant (already compiled)
+        s2 = _schema("guide", 96, 54, "preview")
+        s2.customShaderParameters = dict(s2.customShaderParameters, bigSphereSize=rm.u.float(3.5))
+        got2, _p, _a, want2 = _render_both(c, "guide", s2)
+        np.testing.assert_array_equal(got2["rgba8"], want2)
+        assert ex._spec_streak[hash(s.sdfShaderSource)][1] == 1
+        assert not np.array_equal(got2["rgba8"], frames[0])
+    finally:
+        c.close()
+        ex.reset_specialization_history()
+
+
+def test_variant_cap_unloads_least_recently_used_and_stale_handles_fail_cleanly(monkeypatch):
+    """RMB_VARIANT_CAP bounds the specialised variants per scene; an evicted handle reports an error (never dangles);
+    a new variant starts from the uniform values of the variant used last (GL: uniforms persist per program)."""
+    monkeypatch.setenv("RMB_VARIANT_CAP", "2")
+    c = rm.load_render_job_context(device=0, specialize="always")
+    try:
+        src = scene_source("guide")
+        base = rm.default_custom_settings(src)
+        name = "bigSphereSize"
+        progs = []
+        for k in range(3):
+            spec = dict(base)
+            spec[name] = rm.u.float(float(base[name].data[0]) * (1.0 + 0.125 * k))
+            p = c.program_cache.get_program(src, None, spec)
+            assert isinstance(p, rm.Program), p
+            if k == 0:
+                rm.set_uniform_array(p, "raymarchingStepCountsArray", 1, [7.0, 5.0])
+            progs.append((p, spec))
+        # variant 0 is the least recently used of three: unloaded
+        with pytest.raises(RuntimeError, match="unloaded"):
+            rm.set_uniforms(progs[0][0], {"fov": rm.u.float(1.0)})
+        fb = c.fbo.create(32, 18, 991)
+        assert rm._lib.lib.rmb_render_sample(c.handle, progs[0][0].handle, fb.handle, 0, 0, 32, 18) != 0
+        assert "unloaded" in c.last_error()
+        # variants 1 and 2 inherited the step counts set on variant 0 (through variant 1)
+        s = _schema("guide", 32, 18, "preview")
+        for p, spec in progs[1:]:
+            s.customShaderParameters = spec
+            rm.set_uniforms(p, rm.builtin_uniforms(s, (0.5, 1.0 / 3.0)))
+            rm.set_uniforms(p, spec)
+            rm.set_uniform_matrix4(p, "rotation", list(s.camera.rotation))
+            c.counters(reset=True)
+            assert rm._lib.lib.rmb_render_sample(c.handle, p.handle, fb.handle, 0, 0, 32, 18) == 0, c.last_error()
+            c.sync()
+            evals, px = c.counters()
+            assert px == 32 * 18 and evals <= 7 * px, (evals, px)      # 7 steps, not the 128 of a fresh schema
+        c.fbo.delete(32, 18, 991)
+        # asking again for variant 0 simply rebuilds it
+        p0 = c.program_cache.get_program(src, None, progs[0][1])
+        assert isinstance(p0, rm.Program)
+        rm.set_uniforms(p0, {"fov": rm.u.float(1.0)})
+    finally:
+        c.close()
