@@ -227,11 +227,32 @@ LowerResult lower_scene(const std::string& glsl, const std::set<std::string>& co
     while (i < n) {
         Token& t = T[i];
         if (t.kind == kPP) {
-            // #version / #extension are GLSL-only
+            // #version / #extension are GLSL-only.  The other directives are handed to NVRTC, but only the ones GLSL ES
+            // 3.00 itself has (section 3.4): anything else - #include above all, which would make NVRTC read host files
+            // and quote them in the info log - is the compile error it is in the reference's sandboxed GLSL.  A #define /
+            // #undef may not touch the names the pipeline splices around the scene (rm_*, g_*, RM_*, GLSL_*, __*): a
+            // scene macro could otherwise rewrite the hand-written kernels and silently break their parity.
             size_t p = 1;
             while (p < t.text.size() && (t.text[p] == ' ' || t.text[p] == '\t')) p++;
-            std::string d = t.text.substr(p, 9);
-            if (d.compare(0, 7, "version") == 0 || d.compare(0, 9, "extension") == 0) t.drop = true;
+            size_t q = p;
+            while (q < t.text.size() && (isalpha((unsigned char)t.text[q]) || t.text[q] == '_')) q++;
+            const std::string d = t.text.substr(p, q - p);
+            static const std::set<std::string> allowed = {"", "define", "undef", "if", "ifdef", "ifndef", "else", "elif", "endif",
+                                                          "error", "pragma", "line", "version", "extension"};
+            if (!allowed.count(d)) return fail(t.line, "'#" + d + "' : invalid directive name");
+            if (d == "version" || d == "extension") t.drop = true;
+            if (d == "define" || d == "undef") {
+                size_t a = q;
+                while (a < t.text.size() && (t.text[a] == ' ' || t.text[a] == '\t')) a++;
+                size_t b = a;
+                while (b < t.text.size() && (isalnum((unsigned char)t.text[b]) || t.text[b] == '_')) b++;
+                const std::string name = t.text.substr(a, b - a);
+                auto starts = [&](const char* pre) { return name.compare(0, strlen(pre), pre) == 0; };
+                if (starts("rm_") || starts("g_") || starts("RM_") || starts("GLSL_") || starts("__") || starts("gl_") || starts("GL_") ||
+                    name == "sdfAt" || name == "S" || renames().count(name))
+                    return fail(t.line, "'" + name + "' : reserved built-in macro name");
+                if (d == "define" && !name.empty()) R.macros.insert(name);
+            }
             i++;
             continue;
         }

@@ -27,6 +27,8 @@ struct LowerResult {
                                         // packed types of glsl_pk.h while uniform-only expressions stay float
     std::vector<UniformDecl> uniforms;  // scene-declared uniforms, removed from `body`
     std::set<std::string> functions;    // functions DEFINED at global scope
+    std::set<std::string> macros;       // names the scene #defines: the translation unit #undefs them after the scene text,
+                                        // so that they cannot reach the pipeline code spliced after it
     bool pure = true;                   // no mutable per-invocation state reachable from scene code
     std::string carve_text;             // non-empty when sdf() is a union of `length(..) - K` shapes carved out
                                         // of an outer shape (max(A, -M)): definitions of rm_carve_outer(P) = A

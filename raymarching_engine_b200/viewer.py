@@ -68,6 +68,7 @@ class RealtimeController:
     _previously_switched: bool = False
     _keys: Dict[str, bool] = field(default_factory=dict)
     _accel: Tuple[float, float, float] = (0.0, 0.0, 0.0)
+    _job_frameid: int = 0
 
     def mouse_move(self, movement_x: float, movement_y: float) -> None:                # index.tsx:78-95
         if not self.pointer_locked:
@@ -81,7 +82,13 @@ class RealtimeController:
             return
         self._keys[name.lower()] = down
 
-    def begin_loop(self) -> Tuple[int, int]:                                            # index.tsx:190-233
+    def begin_loop(self) -> Tuple[int, int]:                                            # index.tsx:120-233
+        """One iteration of loop() up to the doRenderJob call: returns (frameid of THIS loop's job, samplesRenderedSoFar
+        handed to makePresenter).  The reference builds testRenderJob - render.frameid included, index.tsx:121-182 -
+        at the top of loop(), BEFORE the new-frame rule increments frameid (:221-231): the loop that resets the sample
+        counter to 1 still accumulates into the OLD frame's buffers, and the fresh buffers are first drawn one loop later,
+        presented with brightness 1/2.  Reproduced as is (bug-compatible; tests/test_viewer_*)."""
+        self._job_frameid = self.frameid                     # what testRenderJob captured
         sp = self.camera_speed
         ax = (sp if self._keys.get("d") else 0.0) - (sp if self._keys.get("a") else 0.0)
         ay = (sp if self._keys.get(" ") else 0.0) - (sp if self._keys.get("shift") else 0.0)
@@ -96,7 +103,7 @@ class RealtimeController:
         self.samples_rendered_so_far += 1
         if should_switch:
             self._previously_switched = True
-        return self.frameid, self.samples_rendered_so_far
+        return self._job_frameid, self.samples_rendered_so_far
 
     def end_loop(self) -> None:                                                         # index.tsx:267-279
         self._mouse_has_moved -= 1
@@ -108,4 +115,4 @@ class RealtimeController:
         """what index.tsx:121-182 copies into the job every frame"""
         schema.camera.position = tuple(self.viewer_position)
         schema.camera.rotation = tuple(float(v) for v in self.camera_rotation)
-        schema.render.frameid = self.frameid
+        schema.render.frameid = self._job_frameid

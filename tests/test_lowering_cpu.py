@@ -182,3 +182,34 @@ def test_varying_lowering_for_the_two_rays_per_lane_kernels(monkeypatch):
     monkeypatch.setenv("RMB_DUAL_STRICT", "1")
     st, log, _, _ = compile_only(scene_source("tree"), _lib.FLAVOUR_EXACT, rm.default_custom_settings(scene_source("tree")))
     assert st != _lib.RMB_OK and "pvec3" in log
+
+
+def test_preprocessor_directives_are_sandboxed():
+    """the scene is sandboxed GLSL ES in the reference.  #include (NVRTC would read host files and quote them
+    in the info log) and any non-GLSL directive are compile errors; macros may not take the names of the pipeline the
+    scene is spliced into; and a legal scene macro ends with the scene text (it is #undef'd before the kernels)."""
+    def translate(src):
+        log = C.create_string_buffer(1 << 16)
+        out = C.create_string_buffer(2 << 20)
+        b = src.encode()
+        st = L.rmb_translate_only(b, len(b), _lib.FLAVOUR_EXACT, None, 0, log, len(log), out, len(out))
+        return st, log.value.decode(), out.value.decode()
+    sdf = "float sdf(vec3 p) { return length(p) - 1.0; }\n"
+    st, log, _ = translate('#include "/etc/passwd"\n' + sdf)
+    assert st == _lib.RMB_ERR_FRAGMENT and log.startswith("ERROR: 0:146:") and "include" in log and "root:" not in log
+    st, log, _ = translate(sdf + "#  include </etc/hostname>\n")
+    assert st == _lib.RMB_ERR_FRAGMENT and "include" in log
+    for bad in ("#import x", "#warning hello", "#include_next <x>", "#assert x"):
+        assert translate(bad + "\n" + sdf)[0] == _lib.RMB_ERR_FRAGMENT, bad
+    for name in ("sdfAt", "g_fma", "rm_carve_outer", "RM_BLOCK_THREADS", "GLSL_FAST", "__launch_bounds__", "gl_FragCoord"):
+        st, log, _ = translate(f"#define {name} 1\n" + sdf)
+        assert st == _lib.RMB_ERR_FRAGMENT and name in log and "reserved" in log, name
+        assert translate(f"#undef {name}\n" + sdf)[0] == _lib.RMB_ERR_FRAGMENT, name
+    # legal directives pass through, and the macro does not outlive the scene
+    src = "#define RADIUS 1.5\n#define lane 7\n#ifdef RADIUS\nfloat sdf(vec3 p) { return length(p) - RADIUS; }\n#else\n#error no radius\n#endif\n"
+    st, log, tu = translate(src)
+    assert st == _lib.RMB_OK, log
+    scene_at, undef_at, kernels_at = tu.index("#define RADIUS 1.5"), tu.index("#undef RADIUS"), tu.rindex("rm_wf_march_preview_kernel")
+    assert scene_at < undef_at < kernels_at and "#undef lane" in tu
+    st, log, _, _ = compile_only(src, want_source=False)      # `lane` is a variable of the march kernel: still compiles
+    assert st == _lib.RMB_OK, log

@@ -770,3 +770,44 @@ def test_variant_cap_unloads_least_recently_used_and_stale_handles_fail_cleanly(
         rm.set_uniforms(p0, {"fov": rm.u.float(1.0)})
     finally:
         c.close()
+
+
+def test_realtime_controller_drives_renders_with_the_reference_frameid_rule(ctx):
+    """the interactive loop of index.tsx:120-283 (viewer.RealtimeController) pumped into the CUDA path.
+    Moving loops bump frameid one loop late and the presenter's brightness is 1 / samplesRenderedSoFar; every presented
+    frame must equal the oracle's, which accumulates per frameid exactly as the framebuffer pool does (new frameid ->
+    cleared set, same frameid -> samples add up)."""
+    from raymarching_engine_b200 import viewer
+    W, H = 96, 54
+    c = viewer.RealtimeController(camera_speed=0.25)
+    s = _schema("guide", W, H, "preview")
+    rm.reset_halton()
+    base = 880000
+    accs, shown, loops = {}, [], 0
+    script = [("w", True), None, ("w", False), None, None, "mouse", None, None, None, None, None, None, None]
+    for ev in script:
+        if isinstance(ev, tuple):
+            c.key(*ev)
+        elif ev == "mouse":
+            c.mouse_move(40.0, -15.0)
+        frameid, samples = c.begin_loop()
+        c.apply_to(s)
+        s.render.frameid = base + frameid
+        sink = {}
+        gen = rm.do_render_job(s, ctx)(rm.make_presenter(samples, sink))
+        try:
+            while True:
+                next(gen)
+        except StopIteration as stop:
+            assert stop.value["success"], stop.value["why"]
+        c.end_loop()
+        acc = accs.setdefault(frameid, pyoracle.Accumulators(W, H))
+        pyoracle.run_job("guide", s, halton_start=loops, acc=acc)
+        want = pyoracle.display(acc, 1.0 / samples)
+        np.testing.assert_array_equal(sink["rgba8"], want, err_msg=f"loop {loops}: frameid {frameid}, samples {samples}")
+        shown.append((frameid, samples))
+        loops += 1
+    # the rule itself: two loops land in frame 0's buffers with brightness 1 (the reference's one-loop-late switch),
+    # a still camera then accumulates 2, 3, ... samples, and the mouse keeps switching for five loops
+    assert shown == [(0, 1), (0, 1), (1, 1), (2, 2), (2, 3), (2, 4), (2, 1), (3, 1), (4, 1), (5, 1), (6, 1), (7, 2), (7, 3)], shown
+    assert len(accs) == 8

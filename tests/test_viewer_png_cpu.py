@@ -48,11 +48,16 @@ def test_new_frame_rule_is_one_loop_late():
     c.key("w", False)
     for i in range(3):
         seq.append(c.begin_loop()); c.end_loop()
-    # loop 0 renders frame 0 while moving; every later loop that FOLLOWS a moving loop starts a new frame
-    assert seq == [(0, 1), (1, 1), (2, 1), (3, 1), (3, 2), (3, 3)]
+    # (frameid of the loop's job, samples handed to the presenter).  Every loop that FOLLOWS a moving loop bumps frameid
+    # and resets the counter - but its own job was built before the bump (index.tsx:121-182 vs :221-231), so it still
+    # draws into the previous frame's buffers; the fresh buffers are first used one loop later
+    assert seq == [(0, 1), (0, 1), (1, 1), (2, 1), (3, 2), (3, 3)]
+    assert c.frameid == 3
     assert c.viewer_position == [0.0, 0.0, 1.5]            # three loops of +z at speed 0.5, identity rotation
     c.requesting_new_frame = True
-    assert c.begin_loop() == (4, 1)
+    assert c.begin_loop() == (3, 1) and c.frameid == 4
+    c.end_loop()
+    assert c.begin_loop() == (4, 2)
 
 
 def test_mouse_look_keeps_switching_for_five_loops_and_moves_along_view():
@@ -61,7 +66,7 @@ def test_mouse_look_keeps_switching_for_five_loops_and_moves_along_view():
     ids = []
     for _ in range(8):
         ids.append(c.begin_loop()[0]); c.end_loop()
-    assert ids == [0, 1, 2, 3, 4, 5, 5, 5]                    # mouseHasMoved counts 5,4,3,2,1 -> five switching loops
+    assert ids == [0, 0, 1, 2, 3, 4, 5, 5]                    # mouseHasMoved counts 5,4,3,2,1 -> five switching loops, one loop late
     c.key("w", True)
     c.begin_loop(); c.end_loop()
     np.testing.assert_allclose(c.viewer_position, [math.sin(0.4), 0.0, math.cos(0.4)], atol=1e-6)
