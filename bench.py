@@ -50,6 +50,18 @@ FLOP_PER_CASTRAY_STEP = 278.0
 # length(p - c) - R = 3 sub + 5 (dot) + 1 sqrt + 1 sub, plus the same 10 / 6 for advance, depth and compares
 FLOP_PER_FAR_PREVIEW_STEP = 20.0
 FLOP_PER_FAR_CASTRAY_STEP = 16.0
+# BASELINE.json config 4 (scenes/mandelbulb.glsl, synthetic - SURVEY.md 8d has no count for it; same convention: FMA = 2,
+# every other operation and every transcendental = 1, uniform-only sub-expressions hoisted).  One trip of the DE loop:
+# length 6 + bailout compare 1 + z.z / r 1 + acos 1 + atan 1 + (pow, * power, fma) 4 + pow 1 + 2 angle products 2 +
+# 2 sin + 2 cos 4 + 2 products 2 + zr * v + position (3 fma) 6 = 29 flop, 9 of them transcendental (in the fast flavour
+# 11 MUFU operations: rsq, rcp, 2 x (lg2 + ex2), 2 sin, 2 cos, rsq of acos); per evaluation the trip that bails out
+# (length + compare, 7) and the tail 0.5 * log(r) * r / dr (4).  The trips per evaluation are data-dependent: measured
+# by the oracle on the workload's own rays (pyoracle.executed_work, cpu_baseline leg), else the pinned figure below
+# (oracle, 320x180, poses 0 / 37 / 101 / 200 of the orbit: 2.44 trips per executed evaluation, 29 evaluations per pixel).
+MANDELBULB_FLOP_PER_DE_TRIP = 29.0
+MANDELBULB_FLOP_PER_EVAL_TAIL = 11.0
+MANDELBULB_MUFU_PER_DE_TRIP = 11.0
+MANDELBULB_DE_TRIPS_PER_EVAL_PINNED = 2.44
 N_POSES = 256
 FLUSH_BYTES = 160 << 20   # > the 126 MB L2 of a B200
 
@@ -171,6 +183,22 @@ def cpu_reference_sample(W, H, mode, band_rows, nthreads=None, scene="guide", co
     px = W * min(band_rows, H)
     secs = (t1 - t0) + (t2 - t1) * (px / (W * H))
     return px / secs / 1e6, secs, cores, f"{W}x{min(band_rows, H)} band of one {W}x{H} {mode}-mode frame, raymarch + display, {cores} threads"
+
+
+def mandelbulb_de_trips_per_eval(counts):
+    """DE-loop trips per executed SDF evaluation of the config-4 workload, from the oracle's early-out analysis of the
+    workload's own camera rays (part of the cpu_baseline leg: loads oracle/liboracle.so)."""
+    sys.path.insert(0, str(ROOT / "oracle"))
+    import pyoracle
+    ho = host_only_modules()
+    src = (ROOT / "scenes" / "mandelbulb.glsl").read_text()
+    custom = ho.default_custom_settings(src)
+    evals = trips = 0
+    for pose in (0, 37, 101, 200):
+        s = make_schema(ho, src, custom, 320, 180, "preview", pose, 0, "mandelbulb", counts or [512.0])
+        e, t = pyoracle.executed_work("mandelbulb", s)
+        evals, trips = evals + e, trips + t
+    return trips / max(evals, 1)
 
 
 def _json_safe(x):
@@ -542,7 +570,17 @@ def run_b200(args):
     sm_max = clocks.get("sm_max_mhz") or 1965.0
     nominal_peak = sm_count * 128 * 2 * sm_max * 1e6 / 1e12
     flop_per_step = FLOP_PER_PREVIEW_STEP if args.mode == "preview" else FLOP_PER_CASTRAY_STEP
-    if args.scene != "guide":
+    de_trips, de_trips_source = None, None
+    if args.scene == "mandelbulb":
+        de_trips, de_trips_source = MANDELBULB_DE_TRIPS_PER_EVAL_PINNED, "pinned (bench.py header)"
+        if rank == 0 and world == 1 and not args.no_cpu_baseline and not args.quick:
+            try:
+                de_trips = mandelbulb_de_trips_per_eval(rig.counts)
+                de_trips_source = "oracle, this run: 320x180 preview, poses 0 / 37 / 101 / 200 of the orbit"
+            except Exception as e:   # noqa: BLE001 - keep the pinned figure
+                de_trips_source += f" (oracle measurement failed: {str(e)[:80]})"
+        flop_per_step = MANDELBULB_FLOP_PER_DE_TRIP * de_trips + MANDELBULB_FLOP_PER_EVAL_TAIL + (10.0 if args.mode == "preview" else 6.0)
+    elif args.scene != "guide":
         flop_per_step = float("nan")    # the algorithmic flop count is defined for the default scene only
     flop_per_far_step = FLOP_PER_FAR_PREVIEW_STEP if args.mode == "preview" else FLOP_PER_FAR_CASTRAY_STEP
     kernel_s = hot_ms * 1e-3
@@ -577,6 +615,18 @@ def run_b200(args):
         "executed_steps_per_px": evals / max(pxs, 1), "registers_per_thread": regs[0], "local_bytes": regs[1],
         "note": "timed alone: a separate pass of frames on ONE context, CUDA events around every march launch, L2 flushed before every frame",
     }
+    if de_trips is not None:
+        # config 4 is transcendental-bound, not FMA-bound: the FP32 figure above is reported for uniformity, the ceiling
+        # that matters is the XU pipe (16 MUFU lanes per SM per clock) in the fast flavour and the fp64 pipe in the exact
+        # one, whose transcendentals are evaluated in binary64 (profiles/r2_ncu_config4_*.txt)
+        mufu_per_eval = MANDELBULB_MUFU_PER_DE_TRIP * de_trips + 2.0      # + log and the division of the tail
+        xu_peak = sm_count * 16 * sm_max * 1e6 / 1e12
+        xu_achieved = (evals_solo - far_solo) * mufu_per_eval / kernel_s / 1e12 if kernel_s > 0 else 0.0
+        roofline["config4"] = {"de_trips_per_eval": de_trips, "de_trips_source": de_trips_source,
+                               "flop_per_de_trip": MANDELBULB_FLOP_PER_DE_TRIP, "flop_per_eval_tail": MANDELBULB_FLOP_PER_EVAL_TAIL,
+                               "mufu_per_de_trip_fast_flavour": MANDELBULB_MUFU_PER_DE_TRIP,
+                               "xu_bound": {"achieved": xu_achieved, "peak": xu_peak, "unit": "T MUFU lane-ops/s", "frac": xu_achieved / xu_peak,
+                                            "applies_to": "fast flavour (the exact flavour evaluates transcendentals in binary64 on the fp64 pipe)"}}
 
     line = {
         "metric": metric_name(args), "value": value, "unit": "Mpx/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

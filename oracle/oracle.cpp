@@ -314,6 +314,9 @@ struct SceneInlineDefault : DefaultMaterials {                      // src/index
 
 // Synthetic divergence-stress scene of BASELINE.json config 4 (NOT in the reference): power-8
 // Mandelbulb distance estimator with in-DE bailout.  Mirrors scenes/mandelbulb.glsl.
+// g_de_iterations: trips of the DE loop on this thread (workload analysis only - bench.py prices an SDF evaluation of
+// config 4 by the iterations it runs; read with orc_de_iterations_reset)
+static thread_local unsigned long long g_de_iterations = 0;
 struct SceneMandelbulb : DefaultMaterials {
     float power = 8.0f, bailout = 2.0f, maxIterations = 12.0f;
     static constexpr int NU = 3;
@@ -325,6 +328,7 @@ struct SceneMandelbulb : DefaultMaterials {
         for (float i = 0.0f; i < maxIterations; i++) {
             r = length(z);
             if (r > bailout) break;
+            g_de_iterations++;
             float theta = acos(z.z / r);
             float phi = atan(z.y, z.x);
             dr = pow(r, power - 1.0f) * power * dr + 1.0f;
@@ -838,6 +842,10 @@ void orc_halton(int b, int n, double* out) {
         out[k] = nn / d;
     }
 }
+
+// DE-loop trips of the Mandelbulb scene executed on the calling thread since the last call (orc_preview_exit_steps runs
+// on the calling thread: evaluations = sum of its output, iterations = this counter)
+unsigned long long orc_de_iterations_reset() { unsigned long long v = g_de_iterations; g_de_iterations = 0; return v; }
 
 int orc_preview_exit_steps(const char* scene, const float* custom, int ncustom, const OrcUniforms* U, int W, int H, int* out) {
 #define X(name, T) if (!strcmp(scene, name)) { exit_steps_t<T>(custom, ncustom, U, W, H, out); return 0; }

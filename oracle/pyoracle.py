@@ -58,6 +58,7 @@ def lib() -> C.CDLL:
         L.orc_f32_to_f16.restype = C.c_uint16
         L.orc_f32_to_f16.argtypes = [C.c_float]
         L.orc_sdf_evals_reset.restype = C.c_ulonglong
+        L.orc_de_iterations_reset.restype = C.c_ulonglong
         L.orc_scene_name.restype = C.c_char_p
         L.orc_materials.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_void_p]
         L.orc_render_sample.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
@@ -158,6 +159,22 @@ def display(acc: Accumulators, brightness: float, nthreads: int | None = None) -
     lib().orc_display(acc.color.ctypes.data_as(C.c_void_p), acc.nd.ctypes.data_as(C.c_void_p), acc.W, acc.H,
                       C.c_float(float(np.float32(brightness))), out.ctypes.data_as(C.c_void_p), nthreads or os.cpu_count() or 1)
     return out
+
+
+def executed_work(scene: str, schema, rand_noise=(0.5, 1.0 / 3.0)):
+    """Workload analysis of one preview-mode sample (orc_preview_exit_steps): (SDF evaluations a bit-exact early-out
+    kernel executes, Mandelbulb DE-loop trips inside them - 0 for the other scenes)."""
+    r = schema.render
+    U = uniforms_from_schema(schema, rand_noise)
+    cu = flatten_custom(scene, schema.customShaderParameters)
+    out = np.zeros((r.height, r.width), np.int32)
+    L = lib()
+    L.orc_de_iterations_reset()
+    st = L.orc_preview_exit_steps(scene.encode(), cu.ctypes.data_as(C.c_void_p) if cu.size else None, int(cu.size), C.byref(U), r.width, r.height,
+                                  out.ctypes.data_as(C.c_void_p))
+    if st != 0:
+        raise RuntimeError(f"oracle exit_steps({scene}) failed: {st}")
+    return int(out.sum()), int(L.orc_de_iterations_reset())
 
 
 def halton_seq(base: int, n: int) -> list:

@@ -170,6 +170,13 @@ RM_HD float exp(float x) { return __expf(x); }
 RM_HD float log(float x) { return __logf(x); }
 RM_HD float exp2(float x) { return exp2f(x); }
 RM_HD float log2(float x) { return __log2f(x); }
+// inverse trigonometry on the FP32 pipe (CUDA's single-precision routines: documented maximum error 2 ulp for
+// asinf / acosf / atan2f, 1 ulp for atanf) instead of the exact flavour's binary64 evaluation: the Mandelbulb DE of
+// BASELINE.json config 4 calls acos + atan once per iteration and was fp64-pipe bound in BOTH flavours
+RM_HD float asin(float x) { return asinf(x); }
+RM_HD float acos(float x) { return acosf(x); }
+RM_HD float atan(float x) { return atanf(x); }
+RM_HD float atan(float y, float x) { return atan2f(y, x); }
 #else
 RM_HD float sin(float x) { return rmx::sin_f(x); }
 RM_HD float cos(float x) { return rmx::cos_f(x); }
@@ -179,11 +186,11 @@ RM_HD float exp(float x) { return rmx::exp_f(x); }
 RM_HD float log(float x) { return rmx::log_f(x); }
 RM_HD float exp2(float x) { return rmx::exp2_f(x); }
 RM_HD float log2(float x) { return rmx::log2_f(x); }
-#endif
 RM_HD float asin(float x) { return rmx::asin_f(x); }
 RM_HD float acos(float x) { return rmx::acos_f(x); }
 RM_HD float atan(float x) { return rmx::atan_f(x); }
 RM_HD float atan(float y, float x) { return rmx::atan2_f(y, x); }
+#endif
 RM_HD float sinh(float x) { return rmx::sinh_f(x); }
 RM_HD float cosh(float x) { return rmx::cosh_f(x); }
 RM_HD float tanh(float x) { return rmx::tanh_f(x); }

@@ -207,7 +207,7 @@ const std::vector<DefaultFunction>& default_material_functions() {
     return v;
 }
 
-LowerResult lower_scene(const std::string& glsl, const std::set<std::string>& constant_names) {
+LowerResult lower_scene(const std::string& glsl, const std::set<std::string>& constant_names, bool heavy_transcendentals) {
     LowerResult R;
     std::string trailing;
     std::vector<Token> T = tokenize(glsl, &trailing);
@@ -294,7 +294,41 @@ LowerResult lower_scene(const std::string& glsl, const std::set<std::string>& co
                     if (locals.count(w) || constant_names.count(w)) continue;
                     ok = false;
                 }
-                if (ok && !locals.empty()) t.text = "_Pragma(\"unroll 32\") for";
+                // Unrolling is what folds pow(uniform, i) / reciprocals of a specialised program at compile time - but in the
+                // exact flavour every transcendental whose argument is NOT such a constant inlines 40-150 instructions of
+                // binary64 arithmetic: a 12-trip Mandelbulb DE unrolled 12 times is a 39 000-instruction kernel that runs
+                // out of the instruction cache (ncu: 16 "no instruction" stalls per issue, 18 % issue utilisation).  Loops
+                // with three or more such calls keep their loop form there.
+                int heavy_calls = 0;
+                if (ok && !locals.empty() && heavy_transcendentals) {
+                    static const std::set<std::string> tr = {"sin", "cos", "tan", "asin", "acos", "atan", "sinh", "cosh", "tanh", "asinh", "acosh",
+                                                             "atanh", "pow", "exp", "log", "exp2", "log2"};
+                    size_t b0 = close + 1, b1 = b0;
+                    if (b0 < n && T[b0].text == "{") {
+                        int bd = 0;
+                        for (b1 = b0; b1 < n; b1++) {
+                            if (T[b1].text == "{") bd++;
+                            if (T[b1].text == "}") { bd--; if (bd == 0) break; }
+                        }
+                    } else {
+                        while (b1 < n && T[b1].text != ";") b1++;
+                    }
+                    for (size_t q = b0; q < b1 && q + 1 < n; q++) {
+                        if (T[q].kind != kIdent || !tr.count(T[q].text) || T[q + 1].text != "(") continue;
+                        // arguments made of literals, loop variables and baked uniforms only: folds once unrolled
+                        bool foldable = true;
+                        int pd = 0;
+                        for (size_t a = q + 1; a < b1; a++) {
+                            if (T[a].text == "(") pd++;
+                            if (T[a].text == ")") { pd--; if (pd == 0) break; }
+                            if (T[a].kind == kIdent && !locals.count(T[a].text) && !constant_names.count(T[a].text) &&
+                                !uniform_type_info(T[a].text, &bt, &bc))
+                                foldable = false;
+                        }
+                        if (!foldable) heavy_calls++;
+                    }
+                }
+                if (ok && !locals.empty()) t.text = heavy_calls >= 3 ? "_Pragma(\"unroll 1\") for" : "_Pragma(\"unroll 32\") for";
             }
         }
         if (brace == 0 && paren == 0 && t.kind == kIdent && at_decl_start) {

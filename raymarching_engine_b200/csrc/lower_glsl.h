@@ -43,7 +43,9 @@ struct LowerResult {
 // A `for` loop whose header mentions only its own loop variable, literals and such constants gets
 // `_Pragma("unroll 32")`, so that specialised programs fully unroll short fractal loops and fold the
 // uniform-only sub-expressions (pow(), reciprocals) at compile time.
-LowerResult lower_scene(const std::string& glsl, const std::set<std::string>& constant_names = {});
+// `heavy_transcendentals`: the flavour evaluates sin / pow / acos ... in binary64 (exact): loops with several such calls on
+// non-constant arguments are NOT unrolled (instruction-cache footprint).
+LowerResult lower_scene(const std::string& glsl, const std::set<std::string>& constant_names = {}, bool heavy_transcendentals = false);
 
 // The seven material functions every program must define and their default bodies
 // (Validate.tsx:18-51), already in lowered form.
