@@ -9,7 +9,7 @@
 // Arithmetic uses the exact policy of glsl_rt.h (single IEEE operations ptxas cannot fuse and
 // the shared rm_math.h exp/pow) so the bytes are identical to the CPU oracle's.
 //
-// Layout: a thread presents four consecutive pixels of a row and writes them with one 128-bit store.
+// Layout: a thread presents one pixel; four neighbouring lanes' bytes leave as one 128-bit store.
 // Rows are this rank's LOCAL rows; the texcoord uses the global row.  The blur reads neighbours from the local buffer, which is only correct when this
 // rank owns the whole frame (n_ranks == 1) or the blur radius is 0 (preview mode);
 // the host gathers the colour plane to one rank before presenting a blurred multi-GPU frame.
@@ -113,36 +113,42 @@ __device__ __forceinline__ unsigned int displayPixel(const float4* __restrict__ 
     return gammaByte(T, base.x) | (gammaByte(T, base.y) << 8) | (gammaByte(T, base.z) << 16) | 0xff000000u;
 }
 
-// Layout: a thread presents 4 horizontally adjacent pixels and writes them as ONE 128-bit store (a warp: four full
-// 128-byte lines); rows whose width is not a multiple of 4 finish with scalar stores.
+// Layout: one pixel per thread, a warp per 32-pixel row segment (a warp reads 32 consecutive float4 texels - fully
+// coalesced - and the lanes of a blurred neighbourhood diverge as little as the scene allows); the RGBA8 results of four neighbouring lanes are collected with
+// shuffles and written by every fourth lane as ONE 128-bit store (a warp: one full 128-byte line).  Rows whose width is
+// not a multiple of 4 use scalar stores.
 __global__ void __launch_bounds__(256) rm_display_kernel(const float4* __restrict__ color, const ushort4* __restrict__ nd,
                                                          uchar4* __restrict__ out, uchar4* __restrict__ gather, int W, int localRows, int H,
                                                          int tileRows, int nRanks, int rank, float brightness) {
     __shared__ float T[256];
     T[threadIdx.x] = threadIdx.x ? __uint_as_float(rm_gamma_bits[threadIdx.x - 1]) : __int_as_float(0xff800000);
     __syncthreads();
-    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    const int ly = blockIdx.y;
-    if (x0 >= W || ly >= localRows) return;
+    // a block presents a 32 x 8 pixel tile, one row segment per warp: the +-16-row taps of a blurred neighbourhood are
+    // shared between the rows of the tile through L1
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int ly = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (ly >= localRows) return;                       // (uniform per warp)
     const int t = ly / tileRows;
     const int gy = (t * nRanks + rank) * tileRows + (ly - t * tileRows);
-    unsigned int px[4];
-    const int n = min(4, W - x0);
-    for (int k = 0; k < n; k++) px[k] = displayPixel(color, nd, T, x0 + k, ly, gy, W, H, tileRows, nRanks, rank, brightness);
-    const size_t idx = (size_t)ly * (size_t)W + (size_t)x0;
+    const unsigned int px = x < W ? displayPixel(color, nd, T, x, ly, gy, W, H, tileRows, nRanks, rank, brightness) : 0u;
+    const int lane = threadIdx.x & 31, q = lane & ~3;
+    const unsigned int p0 = __shfl_sync(0xffffffffu, px, q), p1 = __shfl_sync(0xffffffffu, px, q + 1),
+                       p2 = __shfl_sync(0xffffffffu, px, q + 2), p3 = __shfl_sync(0xffffffffu, px, q + 3);
+    if (x >= W) return;
+    const size_t idx = (size_t)ly * (size_t)W + (size_t)x;
     // fused tile gather (multi-GPU row-tile sharding): the same pixels go straight into the assembled
-    // full frame - usually rank 0's memory mapped over NVLink (CUDA IPC) - at their GLOBAL row.  Full 128-byte
-    // lines per warp, so the peer stores are fully coalesced; no separate collective moves pixels.
-    const size_t gidx = (size_t)gy * (size_t)W + (size_t)x0;
-    if (n == 4 && (W & 3) == 0) {
-        const uint4 v = make_uint4(px[0], px[1], px[2], px[3]);
-        *reinterpret_cast<uint4*>(out + idx) = v;
-        if (gather) *reinterpret_cast<uint4*>(gather + gidx) = v;
-    } else {
-        for (int k = 0; k < n; k++) {
-            reinterpret_cast<unsigned int*>(out)[idx + k] = px[k];
-            if (gather) reinterpret_cast<unsigned int*>(gather)[gidx + k] = px[k];
+    // full frame - usually rank 0's memory mapped over NVLink (CUDA IPC / peer access) - at their GLOBAL row.  Full
+    // 128-byte lines per warp, so the peer stores are fully coalesced; no separate collective moves pixels.
+    const size_t gidx = (size_t)gy * (size_t)W + (size_t)x;
+    if ((W & 3) == 0) {
+        if ((lane & 3) == 0) {                         // x is a multiple of 4 and x + 3 < W
+            const uint4 v = make_uint4(p0, p1, p2, p3);
+            *reinterpret_cast<uint4*>(out + idx) = v;
+            if (gather) *reinterpret_cast<uint4*>(gather + gidx) = v;
         }
+    } else {
+        reinterpret_cast<unsigned int*>(out)[idx] = px;
+        if (gather) reinterpret_cast<unsigned int*>(gather)[gidx] = px;
     }
 }
 
@@ -218,7 +224,7 @@ extern "C" cudaError_t rmb_launch_fp32_peak(float* scratch, int blocks, int iter
 
 extern "C" cudaError_t rmb_launch_display(const void* color, const void* nd, void* rgba8, void* gather, int W, int local_rows, int H,
                                           int tile_rows, int n_ranks, int rank, float brightness, cudaStream_t stream) {
-    dim3 block(256, 1, 1), grid((unsigned)((W + 1023) / 1024), (unsigned)local_rows, 1);    // 4 pixels per thread
+    dim3 block(256, 1, 1), grid((unsigned)((W + 31) / 32), (unsigned)((local_rows + 7) / 8), 1);
     xg::disp::rm_display_kernel<<<grid, block, 0, stream>>>((const float4*)color, (const ushort4*)nd, (uchar4*)rgba8, (uchar4*)gather, W,
                                                             local_rows, H, tile_rows, n_ranks, rank, brightness);
     return cudaGetLastError();
