@@ -264,7 +264,7 @@ def workload_config(args) -> dict:
             "frames_per_step": args.frames_per_step,
             "flavour": args.flavour, "pipeline": args.pipeline, "shard": args.shard if args.gpus > 1 else "none",
             "contexts_per_gpu": args.contexts, "gather": args.gather if (args.gpus > 1 and args.shard == "tiles") else "none",
-            "l2": "flushed between timed iterations: a 160 MiB in-stream device memset on every context's stream before each "
+            "l2": "flushed between timed iterations: a 160 MiB in-stream device memset (the L2 is shared by all streams) before each "
                   "step (= batch of frames), inside the timed region; within a step the frames rotate through the contexts' "
                   "framebuffer sets and ray planes (72 B/px per frame in flight); the kernel-alone roofline pass flushes before "
                   "every frame; e2e alternates two framebuffer sets per context (40 B/px each) and reads every frame back",
@@ -303,9 +303,10 @@ class Rig:
         self.frame_counter = [1 + (7 if tiles else 0) * 1000000]
         self.gather_state = {}
         self.fused = None
-        if tiles and world > 1 and args.gather == "fused":
+        if tiles and world > 1 and args.gather in ("fused", "fused-nccl"):
             from raymarching_engine_b200.sharding import FusedTileGather
-            self.fused = FusedTileGather(self.ctxs, W, H, dist, slots=2 * nctx, blur=(args.mode == "full"))
+            self.fused = FusedTileGather(self.ctxs, W, H, dist, slots=2 * nctx, blur=(args.mode == "full"),
+                                         sync="nccl" if args.gather == "fused-nccl" else "flags")
 
     def pose_of(self, frame):   # weak scaling: rank r renders poses r, r+world, ...; tiles: everyone renders pose `frame`
         return frame if self.tiles else frame * self.world + self.rank
@@ -331,10 +332,9 @@ class Rig:
             self.dist.gather(g["send"], g["recv"], dst=0)
 
     def flush_l2(self, nctx=None):
-        """160 MiB memset on the stream of every context in use (in order with the frames around it)"""
-        for k in range(nctx or self.nctx):
-            with self.torch.cuda.stream(self.streams[k]):
-                self.flush_bufs[k].zero_()
+        """160 MiB device memset (> the 126 MB L2, which all streams share) on the stream the step's first frame goes to"""
+        with self.torch.cuda.stream(self.streams[0]):
+            self.flush_bufs[0].zero_()
 
     def device_frame(self, frame, flush=False, nctx=None):
         """one frame, everything resident in HBM (async): [L2 flush], uniforms, raymarch, display[, gather]"""
@@ -364,7 +364,7 @@ class Rig:
             st = L.rmb_present_device(ctx.handle, fb.handle, 1.0)
             assert st == 0, ctx.last_error()
             if fused:
-                fused.complete(ctx)       # one-element all-reduce: every rank has presented this frame
+                fused.complete(ctx)       # completion flag in stream order (or a one-element all-reduce): every rank has presented
             elif self.tiles and self.world > 1:
                 self._gather_tiles(ctx, stream, fb)
         ctx.fbo.delete(W, H, s.render.frameid)
@@ -384,7 +384,7 @@ class Rig:
 
     def measure_device(self, first_frame, n_frames, frames_per_step=1):
         """n_frames enqueued back to back (the host runs ahead of the GPU); before every step (frames_per_step frames)
-        an in-stream 160 MiB L2 flush on every context's stream, INSIDE the timed region; one start event (GPU idle,
+        an in-stream 160 MiB L2 flush, INSIDE the timed region; one start event (GPU idle,
         recorded on every stream) to the last end event.  Returns (total ms max over ranks, launches, (evals,
         pixel-samples, far evals))."""
         torch = self.torch
@@ -656,10 +656,12 @@ def run_b200(args):
             e3_s, _ = r3.measure_e2e(16, n3, False)
             line["config3_tiles"] = {
                 "workload": f"guide.glsl 3840x2160 preview, interleaved 16-row tiles over {world} GPU(s), gather fused into the display kernel's stores "
-                            f"(peer memory over NVLink; one-element all-reduce per frame orders completion); strong scaling",
+                            f"(peer memory over NVLink; completion ordered by "
+                            f"{'stream-ordered flags in shared pinned memory, no collective' if (r3.fused and r3.fused.sync == 'flags') else 'a one-element all-reduce per frame'}); strong scaling",
                 "value": n3 * 3840 * 2160 / (ms3 * 1e-3) / 1e6, "unit": "Mpx/s", "ms_per_frame": ms3 / n3, "frames": n3, "gather": args.gather if world > 1 else "none",
                 "e2e": {"value": n3 * 3840 * 2160 / e3_s / 1e6, "unit": "Mpx/s", "d2h_bytes_per_frame": 3840 * 2160 * 4, "readback": "RGBA8 on rank 0"},
-                "gpu_launches": launches3, "n_gpus": world, "scaling": "strong"}
+                "gpu_launches": launches3, "n_gpus": world, "scaling": "strong",
+                "completion": (r3.fused.sync if r3.fused else "none")}
             r3.close()
         except Exception as e:   # noqa: BLE001 - the headline must not depend on the extra configuration
             line["config3_tiles"] = {"error": str(e)[:300]}
@@ -725,10 +727,11 @@ def main():
     ap.add_argument("--spp", type=int, default=1, help="samples per pixel per frame (config 5: 16)")
     ap.add_argument("--flavour", default="exact", choices=["exact", "fast"])
     ap.add_argument("--shard", default="poses", choices=["poses", "tiles"])
-    ap.add_argument("--gather", default="fused", choices=["fused", "nccl"],
-                    help="--shard tiles: fused = display kernel stores into rank 0's frame over NVLink (CUDA IPC); nccl = torch.distributed.gather")
+    ap.add_argument("--gather", default="fused", choices=["fused", "fused-nccl", "nccl"],
+                    help="--shard tiles: fused = display kernel stores into rank 0's frame over NVLink (CUDA IPC), completion by stream-ordered "
+                         "flags; fused-nccl = the same stores, completion by a one-element all-reduce; nccl = torch.distributed.gather of the rows")
     ap.add_argument("--pipeline", default="wavefront", choices=["wavefront", "megakernel"])
-    ap.add_argument("--contexts", type=int, default=3, help="contexts (streams) per GPU the independent frames are dealt to")
+    ap.add_argument("--contexts", type=int, default=4, help="contexts (streams) per GPU the independent frames are dealt to")
     ap.add_argument("--e2e-depth", action="store_true", help="the end-to-end arm also reads the fp32 depth plane back (8 B/px instead of 4)")
     ap.add_argument("--config3-steps", type=int, default=4, help="steps of the 4K row-tile configuration measured beside the headline (0 = skip)")
     ap.add_argument("--cpu-band-rows", type=int, default=360)

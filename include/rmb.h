@@ -128,6 +128,28 @@ rmb_status rmb_uniform_set(rmb_program* prog, const char* name, int type, int co
 rmb_status rmb_uniform_set_array(rmb_program* prog, const char* name, int type, int components,
                                  int n_elements, const void* data);
 rmb_status rmb_uniform_matrix4(rmb_program* prog, const char* name, const float* m16_column_major);
+/* The whole built-in uniform record of one sample in ONE call: the values RenderJobExecutor.tsx:212-297 uploads before every
+ * draw (setUniforms record :212-264, the step-count / light arrays :268-291, uniformMatrix4fv :293-297), applied in that
+ * order with the semantics of the single calls above.  SURVEY.md 8b's "one POD FrameUniforms struct"; a host that sets ~25
+ * uniforms per sample through an FFI pays for one crossing instead.  Scene-declared custom uniforms still go by name. */
+typedef struct rmb_frame_uniforms {
+    float blendWithPreviousFactor;
+    float randNoise[2];
+    float position[3];
+    float rotation[16];                 /* column-major, transpose = false */
+    float dofAmount, dofFocalPlaneDistance;
+    int32_t cameraMode;                 /* 0 perspective, 1 orthographic, 2 panoramic */
+    float fov;
+    float reflections, raymarchingSteps, indirectLightingRaymarchingSteps;
+    float aspect, fogDensity, exposure;
+    int32_t blendMode, renderMode;      /* 1 additive; 1 preview */
+    int32_t stepCountsLength;           /* entries of raymarchingStepCountsArray to upload (the reference uploads counts.length) */
+    float raymarchingStepCountsArray[10];
+    int32_t lightCount;
+    float lightPositions[30], lightColors[30], lightSizes[10];
+    int32_t showDofFocalPlane;
+} rmb_frame_uniforms;
+rmb_status rmb_uniforms_set_frame(rmb_program* prog, const rmb_frame_uniforms* u);
 
 /* ---- framebuffer pool ----------------------------------------------------------------------
  * replaces context.fbo.create / context.fbo.delete       renderer/LoadRenderJobContext.tsx:184-249
@@ -184,6 +206,19 @@ rmb_status rmb_display_planes(rmb_ctx* ctx, const void* color_full, const void* 
 rmb_status rmb_ipc_export(void* device_ptr, unsigned char handle64[64]);
 rmb_status rmb_ipc_open(rmb_ctx* ctx, const unsigned char handle64[64], void** device_ptr);
 rmb_status rmb_ipc_close(rmb_ctx* ctx, void* device_ptr);
+
+/* Completion flags for that gather (the alternative to a per-frame collective): 32-bit counters in memory every process of
+ * the box can see - e.g. a POSIX shared-memory segment each process maps and registers with rmb_host_register - written
+ * and awaited IN STREAM ORDER (cuStreamWriteValue32 / cuStreamWaitValue32): a rank's "my rows of frame f are stored" follows
+ * its display kernel, rank 0's stream waits for every rank's counter before it touches the assembled frame, and the other
+ * ranks wait for rank 0's "consumed" counter before they overwrite a frame slot.  No host synchronisation, no NCCL.
+ * `flag`: registered host memory or device memory.  RMB_ERR_GENERAL when the driver lacks stream memory operations. */
+rmb_status rmb_host_register(void* host_ptr, size_t bytes);
+rmb_status rmb_host_unregister(void* host_ptr);
+rmb_status rmb_stream_write_u32(rmb_ctx* ctx, void* flag, uint32_t value);
+/* work enqueued on `ctx` from now on runs after everything enqueued on `other` so far (event record + stream wait) */
+rmb_status rmb_ctx_wait_ctx(rmb_ctx* ctx, rmb_ctx* other);
+rmb_status rmb_stream_wait_geq_u32(rmb_ctx* ctx, void* flag, uint32_t value);
 
 /* ---- inspection (tests, benchmarks) --------------------------------------------------------- */
 /* which: 0 colour (float4), 1 normal+dofRadius (4 x binary16), 2 albedo+depth (4 x binary16),
@@ -272,6 +307,7 @@ rmb_status rmb_group_uniform_set(rmb_group_program* prog, const char* name, int 
 rmb_status rmb_group_uniform_set_array(rmb_group_program* prog, const char* name, int type, int components,
                                        int n_elements, const void* data);
 rmb_status rmb_group_uniform_matrix4(rmb_group_program* prog, const char* name, const float* m16_column_major);
+rmb_status rmb_group_uniforms_set_frame(rmb_group_program* prog, const rmb_frame_uniforms* u);
 /* fbo.create / fbo.delete on every member (each keeps its own rows; pool semantics as rmb_fb_acquire) */
 rmb_group_fb* rmb_group_fb_acquire(rmb_group* group, int width, int height, int64_t frameid);
 void rmb_group_fb_release(rmb_group* group, int width, int height, int64_t frameid);

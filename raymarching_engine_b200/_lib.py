@@ -25,8 +25,9 @@ EXPORTED_SYMBOLS = [
     "rmb_render_sample", "rmb_present", "rmb_present_device", "rmb_present_async", "rmb_present_wait", "rmb_fb_device_ptr", "rmb_fb_plane_bytes",
     "rmb_fb_read", "rmb_fb_write", "rmb_fb_copy_to_device", "rmb_counters_read", "rmb_counters_read3", "rmb_counters_read_all", "rmb_program_has_carve", "rmb_probe_carve", "rmb_probe", "rmb_compile_only", "rmb_translate_only", "rmb_host_alloc", "rmb_device_alloc", "rmb_device_free",
     "rmb_host_free", "rmb_measure_fp32_peak", "rmb_measure_fp32x2_peak", "rmb_owned_rows_below",
+    "rmb_uniforms_set_frame", "rmb_host_register", "rmb_host_unregister", "rmb_stream_write_u32", "rmb_stream_wait_geq_u32", "rmb_ctx_wait_ctx",
     "rmb_group_create", "rmb_group_destroy", "rmb_group_last_error", "rmb_group_size", "rmb_group_ctx", "rmb_group_sync", "rmb_group_program_get",
-    "rmb_group_program_member", "rmb_group_uniform_set", "rmb_group_uniform_set_array", "rmb_group_uniform_matrix4", "rmb_group_fb_acquire",
+    "rmb_group_program_member", "rmb_group_uniform_set", "rmb_group_uniform_set_array", "rmb_group_uniform_matrix4", "rmb_group_uniforms_set_frame", "rmb_group_fb_acquire",
     "rmb_group_fb_release", "rmb_group_fb_member", "rmb_group_render_sample", "rmb_group_present", "rmb_group_present_device",
 ]
 
@@ -37,6 +38,16 @@ class SpecData(C.Union):
 
 class SpecUniform(C.Structure):
     _fields_ = [("name", C.c_char_p), ("type", C.c_int), ("count", C.c_int), ("data", SpecData)]
+
+
+class FrameUniforms(C.Structure):        # rmb_frame_uniforms (include/rmb.h)
+    _fields_ = [("blendWithPreviousFactor", C.c_float), ("randNoise", C.c_float * 2), ("position", C.c_float * 3),
+                ("rotation", C.c_float * 16), ("dofAmount", C.c_float), ("dofFocalPlaneDistance", C.c_float),
+                ("cameraMode", C.c_int32), ("fov", C.c_float), ("reflections", C.c_float), ("raymarchingSteps", C.c_float),
+                ("indirectLightingRaymarchingSteps", C.c_float), ("aspect", C.c_float), ("fogDensity", C.c_float),
+                ("exposure", C.c_float), ("blendMode", C.c_int32), ("renderMode", C.c_int32), ("stepCountsLength", C.c_int32),
+                ("raymarchingStepCountsArray", C.c_float * 10), ("lightCount", C.c_int32), ("lightPositions", C.c_float * 30),
+                ("lightColors", C.c_float * 30), ("lightSizes", C.c_float * 10), ("showDofFocalPlane", C.c_int32)]
 
 
 def _load() -> C.CDLL:
@@ -100,6 +111,12 @@ def _load() -> C.CDLL:
         "rmb_device_alloc": (vp, [vp, sz]),
         "rmb_device_free": (None, [vp, vp]),
         "rmb_host_free": (None, [vp]),
+        "rmb_uniforms_set_frame": (i, [vp, C.POINTER(FrameUniforms)]),
+        "rmb_host_register": (i, [vp, sz]),
+        "rmb_host_unregister": (i, [vp]),
+        "rmb_stream_write_u32": (i, [vp, vp, C.c_uint32]),
+        "rmb_stream_wait_geq_u32": (i, [vp, vp, C.c_uint32]),
+        "rmb_ctx_wait_ctx": (i, [vp, vp]),
         "rmb_group_create": (vp, [C.POINTER(i), i, i]),
         "rmb_group_destroy": (None, [vp]),
         "rmb_group_last_error": (cp, [vp]),
@@ -111,6 +128,7 @@ def _load() -> C.CDLL:
         "rmb_group_uniform_set": (i, [vp, cp, i, i, vp]),
         "rmb_group_uniform_set_array": (i, [vp, cp, i, i, i, vp]),
         "rmb_group_uniform_matrix4": (i, [vp, cp, C.POINTER(f)]),
+        "rmb_group_uniforms_set_frame": (i, [vp, C.POINTER(FrameUniforms)]),
         "rmb_group_fb_acquire": (vp, [vp, i, i, C.c_int64]),
         "rmb_group_fb_release": (None, [vp, i, i, C.c_int64]),
         "rmb_group_fb_member": (vp, [vp, i]),

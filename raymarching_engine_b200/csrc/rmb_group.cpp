@@ -272,6 +272,16 @@ rmb_status rmb_group_uniform_matrix4(rmb_group_program* p, const char* name, con
     return RMB_OK;
 }
 
+rmb_status rmb_group_uniforms_set_frame(rmb_group_program* p, const rmb_frame_uniforms* u) {
+    if (!p || !u) return RMB_ERR_INVALID;
+    for (size_t i = 0; i < p->member.size(); i++) {
+        rmb_status st = rmb_uniforms_set_frame(p->member[i], u);
+        if (st != RMB_OK) return member_fail(p->group, (int)i, st);
+    }
+    p->render_mode = u->renderMode;
+    return RMB_OK;
+}
+
 rmb_group_fb* rmb_group_fb_acquire(rmb_group* g, int width, int height, int64_t frameid) {
     if (!g || width < 1 || height < 1) { gfail(g, RMB_ERR_INVALID, "rmb_group_fb_acquire: bad size"); return nullptr; }
     const auto key = std::make_tuple(width, height, frameid);

@@ -320,21 +320,47 @@ def builtin_uniforms(schema: RenderJobSchema, rand_noise) -> Dict[str, UniformDa
     }
 
 
+def frame_uniforms(schema: RenderJobSchema, rand_noise) -> "_lib.FrameUniforms":
+    """The same record as builtin_uniforms + the array / matrix uploads of RenderJobExecutor.tsx:268-297, as the POD block
+    of rmb_uniforms_set_frame (include/rmb.h): one FFI crossing per sample instead of ~25."""
+    r, cam, mode = schema.render, schema.camera, schema.camera.mode
+    counts = schema.reflectionIterationCounts
+    b = _lib.FrameUniforms()
+    b.blendWithPreviousFactor = r.blendWithPreviousFrameFactor
+    b.randNoise[0], b.randNoise[1] = rand_noise[0], rand_noise[1]
+    b.position[0], b.position[1], b.position[2] = cam.position
+    b.rotation[:] = list(cam.rotation)
+    b.dofAmount, b.dofFocalPlaneDistance = schema.dof.amount, schema.dof.distance
+    b.cameraMode = ["perspective", "orthographic", "panoramic"].index(mode.type) if mode.type in ("perspective", "orthographic", "panoramic") else -1
+    b.fov = mode.fov if mode.type == "perspective" else mode.size if mode.type == "orthographic" else 1
+    b.reflections = len(counts)
+    b.raymarchingSteps = counts[0] if counts else math.nan
+    b.indirectLightingRaymarchingSteps = counts[1] if len(counts) > 1 else (counts[0] if counts else math.nan)
+    b.aspect = r.width / r.height
+    b.fogDensity = schema.fogDensity
+    b.exposure = r.exposure / r.samplesPerPixel
+    b.blendMode = 1 if r.blendMode == "additive" else 0
+    b.renderMode = 1 if r.renderMode == "preview" else 0
+    n = min(len(counts), 10)
+    b.stepCountsLength = n
+    b.raymarchingStepCountsArray[:n] = list(counts[:n])
+    lights = schema.lights
+    b.lightCount = len(lights)
+    for k, l in enumerate(lights[:10]):
+        b.lightPositions[3 * k:3 * k + 3] = list(l.position if l.type == "point" else l.direction)
+        b.lightColors[3 * k:3 * k + 3] = list(l.color)
+        b.lightSizes[k] = l.size if l.type == "point" else 0
+    b.showDofFocalPlane = 1 if schema.dof.showFocusedArea else 0
+    return b
+
+
 def upload_sample_uniforms(program: Program, schema: RenderJobSchema, rand_noise) -> None:
-    """Everything RenderJobExecutor.tsx:212-297 uploads before the draw call, in the same order."""
-    set_uniforms(program, builtin_uniforms(schema, rand_noise))
+    """Everything RenderJobExecutor.tsx:212-297 uploads before the draw call: the built-in record, arrays and matrix as
+    one block (rmb_uniforms_set_frame applies them in the reference's order), then the scene's custom uniforms (:266)."""
+    fn = L.rmb_group_uniforms_set_frame if getattr(program, "is_group", False) else L.rmb_uniforms_set_frame
+    if fn(program.handle, C.byref(frame_uniforms(schema, rand_noise))) != _lib.RMB_OK:
+        raise RuntimeError(f"uniform upload: {program.context.last_error()}")
     set_uniforms(program, schema.customShaderParameters)                                   # :266
-    set_uniform_array(program, "raymarchingStepCountsArray", 1, list(schema.reflectionIterationCounts))   # :268-274
-    if len(schema.lights) > 0:                                                             # :276-291
-        pos, col, size = [], [], []
-        for l in schema.lights:
-            pos += list(l.position if l.type == "point" else l.direction)
-            col += list(l.color)
-            size.append(l.size if l.type == "point" else 0)
-        set_uniform_array(program, "lightPositions", 3, pos)
-        set_uniform_array(program, "lightColors", 3, col)
-        set_uniform_array(program, "lightSizes", 1, size)
-    set_uniform_matrix4(program, "rotation", list(schema.camera.rotation))                 # :293-297
 
 
 PresentFn = Callable[[RenderJobContext, RenderJobSchema, FramebufferInfo, int], None]

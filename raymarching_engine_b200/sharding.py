@@ -61,12 +61,24 @@ class FusedTileGather:
       * blur=True (full mode with depth of field, whose display pass reads +-16 neighbour rows): scatter()
         copies the colour and normal+dofRadius accumulators into full-frame planes, rank 0 runs the
         display pass over them with display_assembled().
-    The only collective is a one-element all-reduce per frame on the contexts' streams (complete()) that
-    orders "every rank has stored its rows".
+    Completion is ordered WITHOUT a collective (sync="flags", the default): 32-bit counters in a POSIX shared-memory
+    segment every rank maps and registers (rmb_host_register), written and awaited in stream order
+    (rmb_stream_write_u32 / rmb_stream_wait_geq_u32 = cuStreamWriteValue32 / cuStreamWaitValue32).  Every use of frame
+    slot s is a generation g of that slot (all ranks see the same sequence of calls, so they count alike):
+      complete():  rank r > 0 writes done[r][s] = g after its stores; rank 0's stream waits done[r][s] >= g for all r;
+      aim()/scatter(): rank r > 0 waits consumed[s] >= g - 1 before it overwrites the slot; rank 0 writes consumed[s'] = g'
+                   for every frame it completed earlier on the same context (all its work for them - the caller's reads
+                   of the assembled frame included - is behind it in stream order; a slot last used on another context
+                   is ordered through an event first, rmb_ctx_wait_ctx).
+    No rank ever waits on the host, and rank r never waits for rank s != 0.  sync="nccl" keeps the earlier variant - a
+    one-element all-reduce per frame on the contexts' streams - as the comparison arm and the fallback when the driver
+    has no stream memory operations.  torch.distributed is used at construction (handle exchange) and teardown only.
 
     contexts: the RenderJobContext(s) of THIS rank; dist: an initialised torch.distributed (NCCL)."""
 
-    def __init__(self, contexts, width: int, height: int, dist, slots: int = 4, blur: bool = False):
+    _MAXS = 64          # frame slots the flag segment has room for
+
+    def __init__(self, contexts, width: int, height: int, dist, slots: int = 4, blur: bool = False, sync: str = "flags"):
         import ctypes as C
         import torch
         self.dist, self.contexts = dist, list(contexts)
@@ -112,15 +124,98 @@ class FusedTileGather:
         self.flag = torch.zeros(1, dtype=torch.float32, device=torch.device("cuda", c0.device))
         self._streams = {id(c): torch.cuda.ExternalStream(c.stream(), device=torch.device("cuda", c.device)) for c in self.contexts}
         self._torch = torch
+        # ---- completion flags
+        self._index = {id(c): k for k, c in enumerate(self.contexts)}
+        self._gen = [0] * slots                         # uses of every slot so far
+        self._cur = {}                                  # context index -> (slot, generation) of its frame in flight
+        self._pending = [[] for _ in self.contexts]     # rank 0: frames completed on a context, consumed[] not yet written
+        self._last_ctx = {}                             # rank 0: slot -> context index of its last use
+        self.sync, self._shm, self._flags_addr = "nccl", None, 0
+        if sync == "flags" and slots <= self._MAXS:
+            from multiprocessing import shared_memory
+            nbytes = 4 * self._MAXS * (self.world + 1)
+            box = [None]
+            if self.rank == 0:
+                self._shm = shared_memory.SharedMemory(create=True, size=nbytes)
+                self._shm.buf[:nbytes] = bytes(nbytes)
+                box = [self._shm.name]
+            dist.broadcast_object_list(box, src=0)
+            if self.rank != 0:
+                self._shm = shared_memory.SharedMemory(name=box[0])
+            self._flags_addr = C.addressof(C.c_char.from_buffer(self._shm.buf))
+            ok = L.rmb_host_register(self._flags_addr, nbytes) == _lib.RMB_OK
+            registered = ok
+            if ok:
+                # probe the stream memory operations once (a write of 0 to one of this rank's own counters)
+                ok = L.rmb_stream_write_u32(c0.handle, self._done(self.rank, 0), 0) == _lib.RMB_OK
+                c0.sync()
+            votes = [None] * self.world
+            dist.all_gather_object(votes, bool(ok))
+            if all(votes):
+                self.sync = "flags"
+            else:
+                if registered:
+                    L.rmb_host_unregister(self._flags_addr)
+                self._close_shm()
+
+    def _done(self, rank: int, slot: int) -> int:
+        return self._flags_addr + 4 * (rank * self._MAXS + slot)
+
+    def _consumed(self, slot: int) -> int:
+        return self._flags_addr + 4 * (self.world * self._MAXS + slot)
+
+    def _close_shm(self) -> None:
+        if self._shm is not None:
+            self._flags_addr = 0
+            shm, self._shm = self._shm, None
+            try:
+                shm.close()
+            except BufferError:
+                pass                                  # a ctypes view is still alive: the segment goes with the process
+            if self.rank == 0:
+                try:
+                    shm.unlink()
+                except FileNotFoundError:
+                    pass
+
+    def _begin(self, context, slot: int) -> None:
+        """flow control of the frame about to be stored into `slot` through `context`"""
+        c = self._index[id(context)]
+        s = slot % self.slots
+        self._gen[s] += 1
+        g = self._gen[s]
+        self._cur[c] = (s, g)
+        if self.sync != "flags":
+            return
+        L = _lib.lib
+
+        def check(st, ctx=context):
+            if st != _lib.RMB_OK:
+                raise RuntimeError(ctx.last_error())
+        if self.rank == 0:
+            other = self._last_ctx.get(s)
+            if other is not None and other != c and any(ps == s for ps, _pg in self._pending[other]):
+                # the slot's previous frame was completed (and is being read) on another context's stream
+                check(L.rmb_ctx_wait_ctx(context.handle, self.contexts[other].handle))
+                check(L.rmb_stream_write_u32(context.handle, self._consumed(s), g - 1))
+                self._pending[other] = [(ps, pg) for ps, pg in self._pending[other] if ps != s]
+            for ps, pg in self._pending[c]:
+                check(L.rmb_stream_write_u32(context.handle, self._consumed(ps), pg))
+            self._pending[c] = []
+            self._last_ctx[s] = c
+        elif g > 1:
+            check(L.rmb_stream_wait_geq_u32(context.handle, self._consumed(s), g - 1))
 
     def aim(self, context, slot: int) -> None:
         """the next present of `context` also writes into frame buffer `slot` (no-blur flow)"""
+        self._begin(context, slot)
         if _lib.lib.rmb_ctx_set_gather_target(context.handle, self.ptrs[slot % self.slots], self.nbytes) != _lib.RMB_OK:
             raise RuntimeError(context.last_error())
 
     def scatter(self, context, fb, slot: int) -> None:
         """blur flow: this rank's rows of the colour and normal+dofRadius accumulators -> rank 0's planes"""
         L = _lib.lib
+        self._begin(context, slot)
         for which, name in ((0, "color"), (1, "nd")):
             if L.rmb_fb_scatter_rows(context.handle, fb.handle, which, self.planes[name][slot % self.slots]) != _lib.RMB_OK:
                 raise RuntimeError(context.last_error())
@@ -134,7 +229,21 @@ class FusedTileGather:
             raise RuntimeError(context.last_error())
 
     def complete(self, context) -> None:
-        """enqueue the per-frame completion collective on `context`'s stream (all ranks, same order)"""
+        """after this rank's stores of the current frame of `context`: order "every rank has stored its rows" before
+        whatever rank 0 enqueues next on that context (all ranks call it, in the same order per context)"""
+        if self.sync == "flags":
+            L = _lib.lib
+            c = self._index[id(context)]
+            sl, g = self._cur[c]
+            if self.rank != 0:
+                if L.rmb_stream_write_u32(context.handle, self._done(self.rank, sl), g) != _lib.RMB_OK:
+                    raise RuntimeError(context.last_error())
+            else:
+                for r in range(1, self.world):
+                    if L.rmb_stream_wait_geq_u32(context.handle, self._done(r, sl), g) != _lib.RMB_OK:
+                        raise RuntimeError(context.last_error())
+                self._pending[c].append((sl, g))
+            return
         with self._torch.cuda.stream(self._streams[id(context)]):
             self.dist.all_reduce(self.flag)
 
@@ -159,6 +268,9 @@ class FusedTileGather:
         for p in self._opened:
             L.rmb_ipc_close(self.contexts[0].handle, p)
         self.dist.barrier()
+        if self.sync == "flags" and self._flags_addr:
+            L.rmb_host_unregister(self._flags_addr)
+        self._close_shm()
         for p in self._owned:
             L.rmb_device_free(self.contexts[0].handle, p)
         self._opened, self._owned = [], []
