@@ -18,6 +18,7 @@
 #include <cctype>
 #include <algorithm>
 #include <cstring>
+#include <functional>
 #include <map>
 
 namespace rmb {
@@ -479,6 +480,10 @@ LowerResult lower_scene(const std::string& glsl, const std::set<std::string>& co
         size_t ea_first = 0, ea_last = 0;           // token range of A
         size_t max_first = 0, max_close = 0;        // `max` .. its ')'
         std::vector<size_t> len_tokens;             // the accepted `length` identifiers
+        // pattern B ("iterated difference", see below): X = max(X, -E) with E a min() tree of sdBox(.., B) calls
+        bool boxes = false;
+        size_t x_init_first = 0, x_init_last = 0;   // initialiser of X (= A)
+        std::map<size_t, size_t> box_sites;         // `sdBox` token -> the ',' that ends its first argument
         // bounded-floor analysis (pass 2): position-independent names of sdf's body, the return statement, and the
         // domain-repetition call sites whose operand is the position parameter itself
         std::set<std::string> clean;
@@ -514,7 +519,7 @@ LowerResult lower_scene(const std::string& glsl, const std::set<std::string>& co
             if (T[k].kind == kPP && !T[k].drop) has_pp = true;
             if (live(k) && T[k].kind == kIdent && !T[k].text.empty() && T[k].text.back() == '&') has_ref_params = true;
             // the helper names must be free
-            if (live(k) && T[k].kind == kIdent && (T[k].text.compare(0, 8, "rm_carve") == 0 || T[k].text == "rm_len0" || T[k].text.compare(0, 7, "rm_plim") == 0 ||
+            if (live(k) && T[k].kind == kIdent && (T[k].text.compare(0, 8, "rm_carve") == 0 || T[k].text == "rm_len0" || T[k].text == "rm_box0" || T[k].text.compare(0, 7, "rm_plim") == 0 ||
                                                        T[k].text.compare(0, 8, "rm_floor") == 0 || T[k].text.compare(0, 6, "rm_rep") == 0)) name_clash = true;
         }
         // the analysis reasons about the built-ins: a scene function of the same name (GLSL ES 3.00 forbids it, C++
@@ -700,6 +705,116 @@ LowerResult lower_scene(const std::string& glsl, const std::set<std::string>& co
                 if (d != 0 || !idents_clean(kf, last)) return n;
                 return first;
             };
+            // ---- pattern B: the iterated difference
+            //     float X = A;  ...  X = max(X, -E);  ...  return X;
+            // with every E a tree of min() over sdBox(<anything>, B) calls whose half-extents B do not depend on the
+            // position (the Menger sponge of the reference's examples: crosses of boxes carved out of a cube, level by
+            // level).  The prelude's sdBox (raymarcher.frag:108-112) is length(max(q, 0)) + min(max(q.x, max(q.y, q.z)), 0)
+            // with q = abs(p) - b: the first term is >= 0, and every non-NaN q_j >= -b_j (abs() >= 0, rounding is
+            // monotonic), so with the NaN-dropping min / max of the pinned semantics the second term is
+            // >= min(0, -max_j b_j) whatever p is - NaN and infinite positions included - and so is the rounded sum.
+            // Hence -E <= rm_box0-bound U_E = max over its boxes of max(0, max_j b_j) (a NaN E is dropped by the outer
+            // max), X never exceeds max(A, U) through these statements, and wherever A > U every max() returns A itself.
+            // rm_carve_bound() is sdf's body with X initialised to -3e38 and each sdBox(.., B) replaced by its lower bound
+            // rm_box0(B): the same statements then compute U with the scene's own arithmetic for B.
+            {
+                size_t semi_b = prev_live(cb);
+                size_t rxb = next_live(ret_tok);
+                const bool ret_is_local = semi_b != n && T[semi_b].text == ";" && rxb < cb && T[rxb].kind == kIdent && locals.count(T[rxb].text) &&
+                                          next_live(rxb) == semi_b && !R.functions.count("sdBox");
+                bool okB = ret_is_local;
+                std::string x = okB ? T[rxb].text : std::string();
+                std::map<size_t, size_t> sites;
+                if (okB) {
+                    Local& XL = locals[x];
+                    okB = XL.type == "float" && XL.depth == 1 && XL.has_init && !XL.counter;
+                    if (okB) {
+                        // A: the parameter, uniforms, literals, pure built-ins and the prelude's sdBox
+                        std::set<std::string> saved = clean;
+                        clean.clear();
+                        clean.insert(carve.param);
+                        for (size_t k = XL.init_first; k <= XL.init_last && k < n && okB; k = next_live(k)) {
+                            if (T[k].kind != kIdent) continue;
+                            size_t pv = prev_live(k);
+                            if (pv != n && T[pv].text == ".") continue;
+                            const std::string& w = T[k].text;
+                            if (uniform_type_info(w, &bt, &bc)) continue;
+                            size_t nx = next_live(k);
+                            const bool call = nx < n && T[nx].text == "(";
+                            if (call) { if (!(pure_builtins.count(w) || w == "sdBox")) okB = false; continue; }
+                            if (!(w == carve.param || uniform_names.count(w))) okB = false;
+                        }
+                        clean = saved;
+                    }
+                    // E := min ( E , E ) | sdBox ( <expr> , B )        (token range, inclusive)
+                    std::function<bool(size_t, size_t)> accept_e = [&](size_t first, size_t last) -> bool {
+                        if (first >= n || last >= n || first > last || T[first].kind != kIdent) return false;
+                        size_t o2 = next_live(first);
+                        if (o2 > last || T[o2].text != "(" || match_close(o2) != last) return false;
+                        size_t cm = n; int cms = 0, d = 0;
+                        for (size_t q2 = next_live(o2); q2 < last; q2 = next_live(q2)) {
+                            const std::string& t2 = T[q2].text;
+                            if (t2 == "(" || t2 == "[") d++;
+                            else if (t2 == ")" || t2 == "]") d--;
+                            else if (d == 0 && t2 == ",") { cms++; cm = q2; }
+                            if (assign_ops.count(t2)) return false;                    // no side effects inside
+                            if (T[q2].kind == kIdent && t2 == x) return false;
+                        }
+                        if (cms != 1) return false;
+                        if (T[first].text == "min") return accept_e(next_live(o2), prev_live(cm)) && accept_e(next_live(cm), prev_live(last));
+                        if (T[first].text != "sdBox") return false;
+                        if (!idents_clean(next_live(cm), prev_live(last))) return false;   // B: position-independent
+                        sites[first] = cm;
+                        return true;
+                    };
+                    // every other mention of X:  X = max ( X , - E ) ;   or   X = max ( - E , X ) ;
+                    for (size_t k = next_live(ob); k < cb && okB; k = next_live(k)) {
+                        if (T[k].kind != kIdent || T[k].text != x || k == locals[x].decl || k == rxb) continue;
+                        { size_t pvf = prev_live(k); if (pvf != n && T[pvf].text == ".") { okB = false; break; } }
+                        size_t pv = prev_live(k);
+                        if (pv == n || !(T[pv].text == ";" || T[pv].text == "{" || T[pv].text == "}" || T[pv].text == ")")) { okB = false; break; }
+                        if (T[pv].text == ")") {
+                            bool hdr = false;
+                            for (auto& h : for_headers) if (h.second == pv) hdr = true;
+                            if (!hdr) { okB = false; break; }
+                        }
+                        size_t eq = next_live(k), mx = next_live(eq), o2 = next_live(mx);
+                        if (o2 >= cb || T[eq].text != "=" || T[mx].text != "max" || T[o2].text != "(") { okB = false; break; }
+                        size_t c2 = match_close(o2);
+                        if (c2 == n || c2 >= cb || T[next_live(c2)].text != ";") { okB = false; break; }
+                        size_t cm = n; int cms = 0;
+                        { int d = 0; for (size_t q2 = next_live(o2); q2 < c2; q2 = next_live(q2)) { const std::string& t2 = T[q2].text; if (t2 == "(" || t2 == "[") d++; else if (t2 == ")" || t2 == "]") d--; else if (d == 0 && t2 == ",") { cms++; cm = q2; } } }
+                        if (cms != 1) { okB = false; break; }
+                        size_t x1f = next_live(o2), x1l = prev_live(cm), x2f = next_live(cm), x2l = prev_live(c2);
+                        size_t ef, el;
+                        if (x1f == x1l && T[x1f].text == x) { ef = x2f; el = x2l; }
+                        else if (x2f == x2l && T[x2f].text == x) { ef = x1f; el = x1l; }
+                        else { okB = false; break; }
+                        if (T[ef].text != "-") { okB = false; break; }
+                        if (!accept_e(next_live(ef), el)) { okB = false; break; }
+                        k = c2;
+                    }
+                    if (okB && sites.empty()) okB = false;
+                    if (okB && writes.count(x)) {
+                        // (every write found above is one of the accepted statements: anything else failed the walk)
+                        for (size_t wtok : writes[x]) {
+                            size_t eq = next_live(wtok);
+                            if (eq >= cb || T[eq].text != "=") okB = false;
+                        }
+                    }
+                }
+                if (okB) {
+                    carve.ok = true;
+                    carve.boxes = true;
+                    carve.clean = clean;
+                    carve.ret_tok = ret_tok; carve.ret_semi = semi_b;
+                    carve.m_name = x;
+                    carve.ea_first = locals[x].init_first; carve.ea_last = locals[x].init_last;
+                    carve.x_init_first = locals[x].init_first; carve.x_init_last = locals[x].init_last;
+                    carve.box_sites = sites;
+                    break;
+                }
+            }
             // ---- the return statement
             size_t semi_end = prev_live(cb);
             if (semi_end == n || T[semi_end].text != ";") break;
@@ -1079,6 +1194,14 @@ LowerResult lower_scene(const std::string& glsl, const std::set<std::string>& co
         for (size_t k = carve.body_open + 1; k < carve.body_close; k++) {
             if (!live(k)) continue;
             bound += ' ';
+            if (carve.boxes) {
+                // pattern B: X starts below everything, every accepted sdBox(arg, B) becomes its lower bound rm_box0(B)
+                if (k == carve.x_init_first) { bound += "-3.0e38f"; k = carve.x_init_last; continue; }
+                auto site = carve.box_sites.find(k);
+                if (site != carve.box_sites.end()) { bound += "rm_box0 ("; k = site->second; continue; }
+                bound += T[k].text;
+                continue;
+            }
             if (k == carve.max_first) { bound += "(-" + carve.m_name + ")"; k = carve.max_close; continue; }
             bound += lens.count(k) ? std::string("rm_len0") : T[k].text;
         }

@@ -75,8 +75,68 @@ def test_accepted_shapes():
     assert has_carve(_scene(end="m = max(-m, length(p) - R); return m;"), compile=True)  # operands swapped, assigned; NVRTC takes it
     assert has_carve(_scene(end="float r = max(length(p) - R, -m); return r;"))
     assert has_carve(_scene("float k = 0.3 * sf / 2.0; float dist = length(d) - k; m = min(dist, m);"))
-    for name in ("sphere-grid", "mandelbulb", "menger-sponge", "tree", "smooth-tree", "rotation-fractal"):
+    for name in ("sphere-grid", "mandelbulb", "tree", "smooth-tree", "rotation-fractal"):
         assert not has_carve(scene_source(name)), name                                    # not of that form
+    # pattern B: boxes carved out of an outer shape level by level (X = max(X, -E), E a min() tree of sdBox calls)
+    assert has_carve(scene_source("menger-sponge"), compile=True)
+    assert has_carve(scene_source("menger-sponge"), rm.default_custom_settings(scene_source("menger-sponge")))
+    assert has_carve(_boxes())
+    assert has_carve(_boxes("x = max(-sdBox(g, vec3(sf)), x);"))                          # operands swapped, a single box
+    assert has_carve(_boxes(init="length(p) - R"))                                         # any outer shape of the position
+
+
+BOXES = """
+uniform float R;
+uniform float s0;
+float sdf(vec3 p) {
+  float x = %s;
+  for (float i = 1.0; i < 4.0; i++) {
+    float sf = pow(s0, i);
+    vec3 g = mod(p, sf * 3.0) - sf * 1.5;
+    %s
+  }
+  return x;
+}
+"""
+
+
+def _boxes(stmt="x = max(x, -min(sdBox(g, vec3(sf * 1.5, sf * 0.5, sf * 0.5)), sdBox(g.zxy, vec3(sf * 0.5, sf * 1.5, sf * 0.5))));",
+           init="sdBox(p + vec3(0.5), vec3(R))"):
+    return BOXES % (init, stmt)
+
+
+@pytest.mark.parametrize("stmt,init", [
+    ("x = max(x, -sdBox(g, vec3(sf * p.x)));", None),                        # half-extents depend on the position
+    ("x = max(x, -sdBox(g, g));", None),
+    ("x = max(x, sdBox(g, vec3(sf)));", None),                               # not a difference
+    ("x = max(x, -sdBox(g, vec3(sf)) * 2.0);", None),
+    ("x = max(x, -max(sdBox(g, vec3(sf)), sdBox(g, vec3(sf * 0.5))));", None),   # an intersection inside: no lower bound from the boxes alone
+    ("x = max(x, -(length(g) - sf));", None),                                # not a box (pattern A handles spheres in its own form)
+    ("x = min(x, -sdBox(g, vec3(sf)));", None),
+    ("x = max(x, -sdBox(g, vec3(sf))); x += 0.01;", None),                   # the accumulator is touched some other way
+    ("x = max(x, -sdBox(g, vec3(sf))) - 0.01;", None),
+    ("float y = x; x = max(x, -sdBox(g, vec3(sf)));", None),
+    ("if (p.x > 0.0) x = max(x, -sdBox(g, vec3(sf)));", None),
+    ("x = max(x, -sdBox(g, vec3(sf = sf * 2.0)));", None),                   # side effect inside
+    ("x = max(x, -sdBox(g * x, vec3(sf)));", None),                          # the accumulator feeds its own term
+    (None, "sdBox(p, vec3(R)) + s0 * sdfFractal(p)"),                        # outer shape calls something the analysis does not know
+    (None, "1.0"),                                                           # (accepted shape, but see below: must still be exact)
+])
+def test_rejected_box_shapes(stmt, init):
+    kw = {}
+    if stmt is not None:
+        kw["stmt"] = stmt
+    if init is not None:
+        kw["init"] = init
+    if init == "1.0":
+        assert has_carve(_boxes(**kw))           # a constant outer shape is a (useless but valid) function of the position
+        return
+    assert not has_carve(_boxes(**kw))
+
+
+def test_box_scene_with_its_own_sdBox_is_rejected():
+    assert not has_carve("float sdBox(vec3 p, vec3 b) { return length(p) - b.x - 10.0; }\n" + _boxes())
+    assert not has_carve(_boxes() + "\nfloat rm_box0(vec3 b) { return 0.0; }\n")
 
 
 @pytest.mark.parametrize("loop_tail,end", [
@@ -156,6 +216,8 @@ struct Frag {
     vec2 texcoord;
     ivec2 rm_texSize;
     template <class V> static float rm_len0(const V&) { return 0.0f; }
+    float rm_box0(const vec3& b) { return -max(0.0f, max(b.x, max(b.y, b.z))); }
+    float sdBox(vec3 p, vec3 b) { vec3 q = abs(p) - b; return length(max(q, 0.0f)) + min(max(q.x, max(q.y, q.z)), 0.0f); }
     float sdfSphere(vec3 position, vec3 center, float radius) { return distance(position, center) - radius; }
 %(scene)s
 };
@@ -193,7 +255,7 @@ def _build_harness(tmp_path, src, values):
     m = re.search(r'#line 1 "scene.glsl"\n(.*?)\n#line \d+ "raymarch_kernel.cuh"', tu, re.S)
     assert m
     scene = m.group(1)
-    assert "rm_carve_outer" in scene and "rm_len0" in scene
+    assert "rm_carve_outer" in scene and ("rm_len0" in scene or "rm_box0" in scene)
     decls = re.findall(r"^__constant__ (\w+) (\w+);$", tu, re.M)
     uniforms = "".join("static %s %s = %s;\n" % (t, nme, _cxx_value(values[nme])) for t, nme in decls if nme in values)
     assert len(uniforms.splitlines()) == len(values)
@@ -226,10 +288,16 @@ def _run(exe, pts):
     return np.frombuffer(r.stdout, np.float32).reshape(-1, 3)
 
 
-@pytest.mark.parametrize("case", ["guide-defaults", "guide-varied", "inline-default"])
+@pytest.mark.parametrize("case", ["guide-defaults", "guide-varied", "inline-default", "menger-sponge", "boxes-varied"])
 def test_far_field_value_is_the_outer_shape_bit_for_bit(tmp_path, case):
     rng = np.random.default_rng(20261017)
-    if case == "inline-default":
+    if case == "menger-sponge":
+        src = scene_source("menger-sponge")
+        values = {k: (v.data[0] if v.count == 1 else tuple(v.data)) for k, v in rm.default_custom_settings(src).items()}
+        centre, radius, expect_U = (-0.5, -0.5, -0.5), 0.9, None
+    elif case == "boxes-varied":
+        src, values, centre, radius, expect_U = _boxes(), {"R": 0.8, "s0": 0.41}, (-0.5, -0.5, -0.5), 1.4, None
+    elif case == "inline-default":
         src, values, centre, radius = scene_source("inline-default"), {}, (0, 0, 0), 5.0
         expect_U = np.float32(0.21) * np.float32(3.0)
     else:
@@ -255,7 +323,8 @@ def test_far_field_value_is_the_outer_shape_bit_for_bit(tmp_path, case):
     # and it is not vacuous: both sides of the bound are well populated, the near side really differs
     assert far.sum() > 50000 and (~far).sum() > 50000
     near_differs = (sdf[~far].view(np.uint32) != A[~far].view(np.uint32)).mean()
-    assert near_differs > 0.2
+    # (spheres carved out of a sphere change most of the near field; the sponge's holes only the inside of its cube)
+    assert near_differs > (0.05 if case in ("menger-sponge", "boxes-varied") else 0.2)
     # non-finite positions included
     assert np.isinf(A[far]).any()
 
@@ -292,6 +361,8 @@ struct FragT {
     vec2 texcoord;
     ivec2 rm_texSize;
     template <class V> static float rm_len0(const V&) { return 0.0f; }
+    float rm_box0(const vec3& b) { return -max(0.0f, max(b.x, max(b.y, b.z))); }
+    float sdBox(vec3 p, vec3 b) { vec3 q = abs(p) - b; return length(max(q, 0.0f)) + min(max(q.x, max(q.y, q.z)), 0.0f); }
     float sdfSphere(vec3 position, vec3 center, float radius) { return distance(position, center) - radius; }
     static float floor_nf(float q, float h2) {
         const float M = 12582912.0f;
