@@ -692,7 +692,7 @@ def run_b200(args):
         if roofline.get("far_field_evals_share", 0) > 0:
             # context for the roofline figure: the same workload with the far-field pipeline off (every ray marched by the
             # one kernel, RMB_CARVE=0), measured the same way in a child process
-            cmd[2] = "exact"
+            cmd[3] = "exact"
             try:
                 out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, RMB_CARVE="0"))
                 f = json.loads(out.stdout.strip().splitlines()[-1])

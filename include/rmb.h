@@ -104,6 +104,9 @@ rmb_status rmb_sync(rmb_ctx* ctx);
 rmb_status rmb_program_get(rmb_ctx* ctx, const char* scene_glsl, size_t scene_len, int flavour,
                            const rmb_spec_uniform* spec, int n_spec, rmb_program** out_program,
                            char* err_type, char* infolog, size_t infolog_cap);
+/* 0 once the variant has been unloaded by the per-scene variant cap (RMB_VARIANT_CAP, least recently used first): the
+ * handle stays valid memory, every call on it reports an error, rmb_program_get rebuilds the variant */
+int rmb_program_is_live(rmb_program* prog);
 /* generated CUDA C++ translation unit (debugging / tests); owned by the program */
 const char* rmb_program_source(rmb_program* prog);
 /* 1 if the program carries the two-rays-per-lane march kernels (packed FP32; every bundled scene without

@@ -111,9 +111,22 @@ class _ProgramCache:
 
     def __init__(self, context: "RenderJobContext"):
         self._c = context
+        self._hits: dict = {}          # (source, flavour, baked values) -> Program: the per-job lookup without an FFI crossing
 
     def get_program(self, scene_source: str, flavour: Optional[int] = None, spec: Optional[Dict[str, UniformData]] = None):
         flavour = self._c.flavour if flavour is None else flavour
+        key = (scene_source, flavour, tuple(sorted((k, v.type, tuple(v.data)) for k, v in spec.items())) if spec else None)
+        hit = self._hits.get(key)
+        if hit is not None and L.rmb_program_is_live(hit.handle):
+            return hit
+        prog = self._get_program(scene_source, flavour, spec)
+        if isinstance(prog, Program):
+            if len(self._hits) >= 64:
+                self._hits.pop(next(iter(self._hits)))
+            self._hits[key] = prog
+        return prog
+
+    def _get_program(self, scene_source: str, flavour: int, spec: Optional[Dict[str, UniformData]]):
         arr, n = _lib.make_spec_array(spec)
         out = C.c_void_p()
         etype = C.create_string_buffer(16)

@@ -4,6 +4,7 @@
 TAG=${1:-r2}
 O=gpurun_out
 mkdir -p $O
+python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > $O/smoke_${TAG}.log 2>&1; tail -2 $O/smoke_${TAG}.log
 ( time python -m pytest tests -m gpu -x -q --durations=8 ) > $O/pytest_${TAG}.log 2>&1; tail -16 $O/pytest_${TAG}.log
 python bench.py > $O/bench_${TAG}_default.json 2> $O/bench_${TAG}_default.err; tail -c 1500 $O/bench_${TAG}_default.json; tail -5 $O/bench_${TAG}_default.err
 python bench.py --impl reference --steps 2 --warmup 1 > $O/bench_${TAG}_reference.json 2> $O/bench_${TAG}_reference.err; tail -c 400 $O/bench_${TAG}_reference.json
