@@ -811,3 +811,26 @@ def test_realtime_controller_drives_renders_with_the_reference_frameid_rule(ctx)
     # a still camera then accumulates 2, 3, ... samples, and the mouse keeps switching for five loops
     assert shown == [(0, 1), (0, 1), (1, 1), (2, 2), (2, 3), (2, 4), (2, 1), (3, 1), (4, 1), (5, 1), (6, 1), (7, 2), (7, 3)], shown
     assert len(accs) == 8
+
+
+def test_present_of_a_fresh_framebuffer_is_the_display_of_zero_accumulators(ctx):
+    """doRenderJob presents before its first sample (RenderJobExecutor.tsx:163-166).  The library fills the canvas
+    directly for a set nothing has been drawn into (opaque black, whatever the brightness) and keeps the clear pending;
+    the bytes must be the display pass's (oracle: display of all-zero accumulators), with and without the depth readback,
+    and the draw that follows must still be the fresh-frame draw (bit-exact accumulators)."""
+    W, H = 96, 54
+    zero = pyoracle.Accumulators(W, H)
+    for k, brightness in enumerate((1.0, 0.25, float("inf"), float("nan"), 0.0)):
+        want = pyoracle.display(zero, brightness)
+        assert want[..., 3].min() == 255 and want[..., :3].max() == 0
+        fb = ctx.fbo.create(W, H, 660000 + k)
+        rgba, depth = ctx.present(fb, brightness, want_depth=(k % 2 == 0))
+        np.testing.assert_array_equal(rgba, want)
+        if depth is not None:
+            assert not depth.any()
+        rgba2, _ = ctx.present(fb, brightness, want_depth=False)          # again, still nothing drawn
+        np.testing.assert_array_equal(rgba2, want)
+        ctx.fbo.delete(W, H, 660000 + k)
+    s = _schema("guide", W, H, "preview")
+    got, planes, acc, want = _render_both(ctx, "guide", s)
+    _assert_bit_exact(got, planes, acc, want)
