@@ -194,11 +194,16 @@ class FusedTileGather:
                 raise RuntimeError(ctx.last_error())
         if self.rank == 0:
             other = self._last_ctx.get(s)
-            if other is not None and other != c and any(ps == s for ps, _pg in self._pending[other]):
-                # the slot's previous frame was completed (and is being read) on another context's stream
-                check(L.rmb_ctx_wait_ctx(context.handle, self.contexts[other].handle))
-                check(L.rmb_stream_write_u32(context.handle, self._consumed(s), g - 1))
-                self._pending[other] = [(ps, pg) for ps, pg in self._pending[other] if ps != s]
+            if other is not None and other != c:
+                # the slot's previous frame was completed (and read) on ANOTHER context's stream of this rank
+                if any(ps == s for ps, _pg in self._pending[other]):
+                    # ... and not released yet: order this stream behind that one, release the slot here
+                    check(L.rmb_ctx_wait_ctx(context.handle, self.contexts[other].handle))
+                    check(L.rmb_stream_write_u32(context.handle, self._consumed(s), g - 1))
+                    self._pending[other] = [(ps, pg) for ps, pg in self._pending[other] if ps != s]
+                else:
+                    # ... whose stream has released it (or will): this stream's stores wait for that release too
+                    check(L.rmb_stream_wait_geq_u32(context.handle, self._consumed(s), g - 1))
             for ps, pg in self._pending[c]:
                 check(L.rmb_stream_write_u32(context.handle, self._consumed(ps), pg))
             self._pending[c] = []
