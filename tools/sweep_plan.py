@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--mode", default="preview")
     ap.add_argument("--steps", type=int, default=12)
     ap.add_argument("--flavour", default="exact")
+    ap.add_argument("--ranks", type=int, default=1, help="emulate one rank of an N-rank row-tile split (rank 0's tiles only): the per-GPU work of --shard tiles")
     ap.add_argument("plans", nargs="+")
     a = ap.parse_args()
     import torch
@@ -29,7 +30,7 @@ def main():
     import raymarching_engine_b200 as rm
     L = rm._lib.lib
     flavour = rm.FLAVOUR_FAST if a.flavour == "fast" else rm.FLAVOUR_EXACT
-    ctx = rm.load_render_job_context(device=0, flavour=flavour)
+    ctx = rm.load_render_job_context(device=0, rank=0, n_ranks=a.ranks, tile_rows=16, flavour=flavour, specialize="always")
     src = (ROOT / "scenes" / "guide.glsl").read_text()
     custom = rm.default_custom_settings(src)
     prog = ctx.program_cache.get_program(src, None, custom)
