@@ -45,6 +45,11 @@ def test_fails_loudly_without_a_gpu_or_with_bad_arguments():
     if not torch.cuda.is_available():
         assert rm.load_render_job_context(device=0) is None
         assert "no CPU fallback" in rm.context_error()
+        assert rm.load_render_job_group([0, 0]) is None and "no CPU fallback" in rm.group_error()    # device groups likewise
     assert _lib.lib.rmb_ctx_create(0, 3, 2, 16) is None           # rank >= n_ranks
     assert _lib.lib.rmb_render_sample(None, None, None, 0, 0, 1, 1) == _lib.RMB_ERR_INVALID
     assert _lib.lib.rmb_abi_version() == 1
+    assert _lib.lib.rmb_group_create(None, 0, 16) is None and _lib.lib.rmb_group_size(None) == 0
+    assert _lib.lib.rmb_group_render_sample(None, None, None, 0, 0, 1, 1) == _lib.RMB_ERR_INVALID
+    assert _lib.lib.rmb_uniforms_set_frame(None, None) == _lib.RMB_ERR_INVALID
+    assert _lib.lib.rmb_stream_write_u32(None, None, 0) == _lib.RMB_ERR_INVALID and _lib.lib.rmb_program_is_live(None) == 0
