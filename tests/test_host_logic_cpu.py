@@ -134,3 +134,44 @@ def test_orbit_path_pose_zero_is_the_reference_view():
         fwd = np.array([rot[8], rot[9], rot[10]])
         to_centre = np.array([0, 0, 10]) - np.array(pos)
         assert np.allclose(fwd, to_centre / np.linalg.norm(to_centre)) and abs(np.linalg.norm(to_centre) - 10) < 1e-9
+
+
+def test_frame_uniform_block_carries_the_same_record_as_the_per_name_uploads():
+    """rmb_uniforms_set_frame's POD block (executor.frame_uniforms) against builtin_uniforms + the array / matrix uploads of
+    RenderJobExecutor.tsx:212-297, value by value after the float32 conversion both paths apply."""
+    import ctypes as C
+    from raymarching_engine_b200 import executor as ex
+    src = scene_source("guide")
+    f32 = lambda v: C.c_float(v).value                                    # noqa: E731
+    for mode, cam in (("preview", rm.Perspective(1.5)), ("full", rm.Orthographic(2.25)), ("full", rm.Panoramic())):
+        s = rm.default_schema(src, rm.default_custom_settings(src), width=640, height=360, renderMode=mode, samplesPerPixel=3,
+                              blendMode="mix" if mode == "full" else "additive")
+        s.camera.mode = cam
+        s.camera.position = (0.1, -2.5, 3.75)
+        s.camera.rotation = tuple(0.01 * k for k in range(16))
+        s.dof.showFocusedArea = mode == "full"
+        s.fogDensity = 0.125
+        s.reflectionIterationCounts = [96, 48, 24]
+        if mode == "full":
+            s.lights = [rm.default_light(), rm.SunLight(direction=(0.0, -1.0, 0.5), color=(1.0, 0.5, 0.25))]
+        noise = (0.625, 1.0 / 9.0)
+        rec = ex.builtin_uniforms(s, noise)
+        b = ex.frame_uniforms(s, noise)
+        for name, u in rec.items():
+            if name in ("previousColor", "previousNormalAndDofRadius", "previousAlbedoAndDepth"):
+                continue                                                   # sampler units: constants inside the library
+            got = getattr(b, name)
+            got = list(got) if hasattr(got, "__len__") else [got]
+            want = [f32(v) if u.type == "f" else int(v) for v in u.data]
+            if any(isinstance(w, float) and math.isnan(w) for w in want):
+                assert all(math.isnan(g) for g in got), name
+            else:
+                assert got == want, (name, got, want)
+        assert list(b.rotation) == [f32(v) for v in s.camera.rotation]
+        assert b.stepCountsLength == 3 and list(b.raymarchingStepCountsArray)[:3] == [96.0, 48.0, 24.0]
+        assert b.lightCount == len(s.lights)
+        for k, l in enumerate(s.lights):
+            v = l.position if l.type == "point" else l.direction
+            assert list(b.lightPositions)[3 * k:3 * k + 3] == [f32(x) for x in v]
+            assert list(b.lightColors)[3 * k:3 * k + 3] == [f32(x) for x in l.color]
+            assert b.lightSizes[k] == f32(l.size if l.type == "point" else 0)
