@@ -126,6 +126,14 @@ static napi_value UniformMatrix4(napi_env env, napi_callback_info info) {
     free(name); return mk_i32(env, st);
 }
 
+/* uniformsSetFrame(program, TypedArray over an rmb_frame_uniforms block): the whole per-sample upload of
+ * RenderJobExecutor.tsx:212-297 in one crossing (include/rmb.h; a DataView / Float32Array + Int32Array over one
+ * ArrayBuffer of sizeof(rmb_frame_uniforms) bytes, fields in declaration order) */
+static napi_value UniformsSetFrame(napi_env env, napi_callback_info info) {
+    ARGS(2);
+    return mk_i32(env, rmb_uniforms_set_frame((rmb_program*)ext(env, argv[0]), (const rmb_frame_uniforms*)typed(env, argv[1])));
+}
+
 /* fbAcquire(ctx, w, h, frameid) -> external | undefined; fbRelease(ctx, w, h, frameid)   LoadRenderJobContext.tsx:184-249 */
 static napi_value FbAcquire(napi_env env, napi_callback_info info) {
     ARGS(4);
@@ -210,6 +218,10 @@ static napi_value GroupUniformMatrix4(napi_env env, napi_callback_info info) {
     rmb_status st = rmb_group_uniform_matrix4((rmb_group_program*)ext(env, argv[0]), name, (const float*)typed(env, argv[2]));
     free(name); return mk_i32(env, st);
 }
+static napi_value GroupUniformsSetFrame(napi_env env, napi_callback_info info) {
+    ARGS(2);
+    return mk_i32(env, rmb_group_uniforms_set_frame((rmb_group_program*)ext(env, argv[0]), (const rmb_frame_uniforms*)typed(env, argv[1])));
+}
 static napi_value GroupFbAcquire(napi_env env, napi_callback_info info) {
     ARGS(4);
     return mk_ext(env, rmb_group_fb_acquire((rmb_group*)ext(env, argv[0]), i32(env, argv[1]), i32(env, argv[2]), (int64_t)f64(env, argv[3])));
@@ -250,13 +262,13 @@ static napi_value DisplayPlanes(napi_env env, napi_callback_info info) {
 static napi_value Init(napi_env env, napi_value exports) {
     EXPORT("ctxCreate", CtxCreate); EXPORT("ctxDestroy", CtxDestroy); EXPORT("lastError", LastError);
     EXPORT("programGet", ProgramGet); EXPORT("uniformSet", UniformSet); EXPORT("uniformSetArray", UniformSetArray);
-    EXPORT("uniformMatrix4", UniformMatrix4); EXPORT("fbAcquire", FbAcquire); EXPORT("fbRelease", FbRelease);
+    EXPORT("uniformMatrix4", UniformMatrix4); EXPORT("uniformsSetFrame", UniformsSetFrame); EXPORT("fbAcquire", FbAcquire); EXPORT("fbRelease", FbRelease);
     EXPORT("fbLocalRows", FbLocalRows); EXPORT("renderSample", RenderSample); EXPORT("present", Present);
     EXPORT("presentAsync", PresentAsync); EXPORT("presentWait", PresentWait); EXPORT("sync", Sync);
     EXPORT("groupCreate", GroupCreate); EXPORT("groupDestroy", GroupDestroy); EXPORT("groupLastError", GroupLastError);
     EXPORT("groupSize", GroupSize); EXPORT("groupSync", GroupSync); EXPORT("groupProgramGet", GroupProgramGet);
     EXPORT("groupUniformSet", GroupUniformSet); EXPORT("groupUniformSetArray", GroupUniformSetArray);
-    EXPORT("groupUniformMatrix4", GroupUniformMatrix4); EXPORT("groupFbAcquire", GroupFbAcquire);
+    EXPORT("groupUniformMatrix4", GroupUniformMatrix4); EXPORT("groupUniformsSetFrame", GroupUniformsSetFrame); EXPORT("groupFbAcquire", GroupFbAcquire);
     EXPORT("groupFbRelease", GroupFbRelease); EXPORT("groupRenderSample", GroupRenderSample); EXPORT("groupPresent", GroupPresent);
     EXPORT("setGatherTarget", SetGatherTarget); EXPORT("fbScatterRows", FbScatterRows); EXPORT("displayPlanes", DisplayPlanes);
     return exports;
